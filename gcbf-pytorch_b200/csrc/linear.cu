@@ -1,0 +1,88 @@
+// C-ABI dispatch of the linear layers (K3): picks the tcgen05 3xTF32 kernel when the shape qualifies,
+// otherwise the exact-fp32 SIMT kernel.  Reference op site: gcbf/nn/mlp.py:44-47 (nn.Linear + ReLU chain).
+#include "common.cuh"
+
+namespace gcbf {
+int launch_simt_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma,
+                    float* Y, int ldy, int M, int N, int K, int act, cudaStream_t st);
+int launch_simt_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma,
+                      const float* relu_src, int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate,
+                      cudaStream_t st);
+int launch_simt_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw,
+                      float* db, int M, int N, int K, int accumulate, cudaStream_t st);
+#ifdef GCBF_WITH_TCGEN05
+bool tc_fwd_supported(int ldx, int ldw, int ldy, int M, int N, int K);
+int launch_tc_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
+                  int ldy, int M, int N, int K, int act, cudaStream_t st);
+bool tc_dgrad_supported(int lddz, int ldw, int lddx, int M, int N, int K);
+int launch_tc_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src,
+                    int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
+bool tc_wgrad_supported(int lddz, int ldx, int lddw, int M, int N, int K);
+int launch_tc_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw,
+                    float* db, int M, int N, int K, int accumulate, cudaStream_t st);
+#endif
+}  // namespace gcbf
+
+using namespace gcbf;
+
+extern "C" int gcbf_has_tcgen05(void) {
+#ifdef GCBF_WITH_TCGEN05
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+extern "C" int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias,
+                               const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act, int impl,
+                               void* stream) {
+  GCBF_REQUIRE(M >= 0 && N > 0 && K > 0 && ldx >= K && ldw >= K && ldy >= N, "gcbf_linear_fwd: bad sizes M=%d N=%d K=%d", M, N, K);
+  GCBF_REQUIRE(act >= GCBF_ACT_NONE && act <= GCBF_ACT_TANH, "gcbf_linear_fwd: act %d", act);
+  if (M == 0) return GCBF_OK;
+  GCBF_REQUIRE(X && W && Y, "gcbf_linear_fwd: null pointer");
+  cudaStream_t st = as_stream(stream);
+#ifdef GCBF_WITH_TCGEN05
+  if (impl != 1 && tc_fwd_supported(ldx, ldw, ldy, M, N, K))
+    return launch_tc_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
+#endif
+  if (impl == 2) { set_error("gcbf_linear_fwd: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  return launch_simt_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
+}
+
+extern "C" int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma,
+                                    const float* relu_src, int ld_relu, float* dX, int lddx, int M, int N, int K,
+                                    int accumulate, int impl, void* stream) {
+  GCBF_REQUIRE(M >= 0 && N > 0 && K > 0 && lddz >= N && ldw >= K && lddx >= K, "gcbf_linear_bwd_data: bad sizes M=%d N=%d K=%d", M, N, K);
+  GCBF_REQUIRE(!relu_src || ld_relu >= K, "gcbf_linear_bwd_data: ld_relu");
+  if (M == 0) return GCBF_OK;
+  GCBF_REQUIRE(dZ && W && dX, "gcbf_linear_bwd_data: null pointer");
+  cudaStream_t st = as_stream(stream);
+#ifdef GCBF_WITH_TCGEN05
+  if (impl != 1 && tc_dgrad_supported(lddz, ldw, lddx, M, N, K))
+    return launch_tc_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
+#endif
+  if (impl == 2) { set_error("gcbf_linear_bwd_data: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  return launch_simt_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
+}
+
+extern "C" int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma,
+                                      float* dW, int lddw, float* db, int M, int N, int K, int accumulate, int impl,
+                                      void* stream) {
+  GCBF_REQUIRE(M >= 0 && N > 0 && K > 0 && lddz >= N && ldx >= K && lddw >= K, "gcbf_linear_bwd_weight: bad sizes M=%d N=%d K=%d", M, N, K);
+  GCBF_REQUIRE(dW, "gcbf_linear_bwd_weight: null dW");
+  cudaStream_t st = as_stream(stream);
+  if (M == 0) {
+    if (!accumulate) {
+      GCBF_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)K * 4, N, st));
+      if (db) GCBF_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * 4, st));
+    }
+    return GCBF_OK;
+  }
+  GCBF_REQUIRE(dZ && X, "gcbf_linear_bwd_weight: null pointer");
+#ifdef GCBF_WITH_TCGEN05
+  if (impl != 1 && tc_wgrad_supported(lddz, ldx, lddw, M, N, K))
+    return launch_tc_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);
+#endif
+  if (impl == 2) { set_error("gcbf_linear_bwd_weight: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  return launch_simt_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);
+}

@@ -1,0 +1,105 @@
+"""ctypes binding of libgcbf_b200.so (C ABI declared in include/gcbf_b200.h).
+
+The library is loaded lazily on first use.  There is NO fallback: if the shared object is missing or a
+call fails, a RuntimeError is raised (the product path must never silently run on the CPU).
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_ulonglong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libgcbf_b200.so')
+_lib = None
+
+
+class EnvCfg(ctypes.Structure):
+    """mirror of `gcbf_env_cfg`"""
+    _fields_ = [('env', c_int32), ('num_graphs', c_int32), ('nodes_per_graph', c_int32), ('num_agents', c_int32),
+                ('agent_radius', c_double), ('speed_limit', c_double), ('dist2goal', c_double), ('dt', c_double)]
+
+
+P = c_void_p  # every device pointer travels as void*
+_SIGS = {
+    'gcbf_last_error': (c_char_p, []),
+    'gcbf_abi_version': (c_int, []),
+    'gcbf_has_tcgen05': (c_int, []),
+    'gcbf_radius_graph_count': (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P]),
+    'gcbf_radius_graph_fill': (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P, c_int64, P]),
+    'gcbf_rowptr_from_targets': (c_int, [P, c_int64, c_int, P, P, P]),
+    'gcbf_edge_attr_fwd': (c_int, [c_int, P, c_int, P, c_int64, P, P]),
+    'gcbf_edge_attr_bwd': (c_int, [c_int, P, c_int, P, c_int64, P, P, P]),
+    'gcbf_edge_input_fwd': (c_int, [P, c_int, P, c_int, P, c_int64, P, c_int, P]),
+    'gcbf_linear_fwd': (c_int, [P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'gcbf_linear_bwd_data': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'gcbf_linear_bwd_weight': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'gcbf_act_bwd': (c_int, [P, P, P, c_int64, c_int, P]),
+    'gcbf_attn_aggr_fwd': (c_int, [P, c_int, P, P, c_int, c_int, P, P, c_int, P]),
+    'gcbf_attn_aggr_bwd': (c_int, [P, c_int, P, P, c_int, c_int, P, c_int, P, c_int, P, c_int, P]),
+    'gcbf_rows_gather': (c_int, [P, c_int, P, P, c_int, c_int64, c_int, P]),
+    'gcbf_rows_scatter': (c_int, [P, c_int, P, P, c_int, c_int64, c_int, P]),
+    'gcbf_copy2d': (c_int, [P, c_int, P, c_int, c_int64, c_int, P]),
+    'gcbf_u_ref': (c_int, [POINTER(EnvCfg), P, c_int, P, c_int, P, P, P]),
+    'gcbf_step_fwd': (c_int, [POINTER(EnvCfg), P, c_int, P, P, c_int, P, c_int, P, P, P]),
+    'gcbf_step_bwd': (c_int, [POINTER(EnvCfg), P, c_int, P, P, P]),
+    'gcbf_masks': (c_int, [POINTER(EnvCfg), P, c_int, P, P, P, P]),
+    'gcbf_loss_partials': (c_int, [P, P, P, P, c_int, P, P, c_int64, c_float, c_float, c_float, P, P, P]),
+    'gcbf_loss_grads': (c_int, [P, P, P, P, c_int, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float,
+                                c_float, P, P, P, P, P, P]),
+    'gcbf_pair_count': (c_int, [P, c_int64, P, c_int64, c_float, P, P]),
+    'gcbf_sn_workspace_floats': (c_size_t, [c_int, c_int]),
+    'gcbf_sn_power_iter': (c_int, [P, c_int, c_int, c_int, P, P, P, P, P]),
+    'gcbf_sn_grad_fixup': (c_int, [P, c_int, P, c_int, c_int, c_int, P, P, P, P, P]),
+    'gcbf_grad_sumsq': (c_int, [P, c_int64, P, P]),
+    'gcbf_clip_adam': (c_int, [P, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, c_double, c_int, P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def library_available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not found: build it with `python gcbf-pytorch_b200/csrc/build.py` '
+                '(gcbf_b200 has no CPU / eager fallback)')
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().gcbf_last_error()
+        raise RuntimeError(f'{what} failed (code {rc}): {msg.decode() if msg else ""}')
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point on the current CUDA stream and raise on error."""
+    check(getattr(lib(), name)(*args, stream()), name)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('gcbf_b200 ops need CUDA tensors: there is no CPU fallback '
+                               '(build container has no GPU; run under gpurun)')

@@ -1,0 +1,237 @@
+"""GCBF: CBF network + actor + the train step of reference gcbf/algo/gcbf.py:64-309 on the sm_100a kernels.
+
+What changes relative to the reference's `update` body (results identical, see tests/test_parity_gpu.py):
+  * safe/unsafe masks and the re-linked radius graphs are ONE kernel launch over the whole batch instead of
+    per-graph Python loops (gcbf.py:168, 180, 195-199);
+  * the four losses, their gradients w.r.t. (h, h_next, actions) and the accuracies come from two small
+    kernels (ops: gcbf_loss_partials / gcbf_loss_grads) with an optional all-reduce of the 9 partial sums in
+    between, so environment-parallel ranks reproduce the single-process masked means;
+  * parameters and gradients of both nets live in ONE flat fp32 bucket: a single NCCL all-reduce, then
+    global-norm clip + Adam as one fused kernel per net (gcbf.py:220-226);
+  * the M x M broadcast of `acc/derivative` (gcbf.py:209) is an exact pair count, not an M x M temporary.
+"""
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import _C
+from ..controller import GNNController
+from ..data import Batch, Data, agent_row_index
+from ..nn import MLP, CBFGNNLayer, GraphSequential
+from .base import Algorithm
+from .buffer import Buffer
+
+
+class CBFGNN(nn.Module):
+    """h(x): CBFGNNLayer(out=1024) -> agent rows -> MLP(1024 -> 512,128,32 -> 1, Tanh); reference gcbf.py:21-61."""
+
+    def __init__(self, num_agents: int, node_dim: int, edge_dim: int, phi_dim: int):
+        super().__init__()
+        self.num_agents = num_agents
+        self.feat_transformer = GraphSequential(
+            CBFGNNLayer(node_dim=node_dim, edge_dim=edge_dim, output_dim=1024, phi_dim=phi_dim))
+        self.feat_2_CBF = MLP(in_channels=1024, out_channels=1, hidden_layers=(512, 128, 32),
+                              output_activation=nn.Tanh())
+
+    def forward(self, data) -> Tensor:
+        layer = self.feat_transformer.module_0
+        return layer.run(data.x, data.edge_attr, data.edge_index, row_index=agent_row_index(data), head=self.feat_2_CBF)
+
+    def attention(self, data) -> Tensor:
+        return self.feat_transformer.module_0.attention(data)
+
+
+class _FlatBucket:
+    """All parameters of a list of modules re-homed into one flat fp32 buffer (and their .grad into a second
+    one), so the gradient all-reduce is a single collective and clip+Adam a single pass per net."""
+
+    def __init__(self, modules: List[nn.Module], device):
+        self.ranges = []
+        params = []
+        for m in modules:
+            ps = [p for p in m.parameters()]
+            start = sum(p.numel() for p in params)
+            params += ps
+            self.ranges.append((start, sum(p.numel() for p in params)))
+        total = sum(p.numel() for p in params)
+        self.flat = torch.empty(total, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=device, dtype=torch.float32)
+        self.exp_avg = torch.zeros(total, device=device, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(total, device=device, dtype=torch.float32)
+        off = 0
+        for p in params:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + n].view(p.shape)
+            p.grad = self.grad[off:off + n].view(p.shape)
+            off += n
+        self.params = params
+        self.sumsq = torch.zeros(len(modules), device=device, dtype=torch.float64)
+        self.step = 0
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+class GCBF(Algorithm):
+
+    def __init__(self, env, num_agents: int, node_dim: int, edge_dim: int, action_dim: int, device: torch.device,
+                 batch_size: int = 500, params: Optional[dict] = None):
+        super().__init__(env=env, num_agents=num_agents, node_dim=node_dim, edge_dim=edge_dim, action_dim=action_dim,
+                         device=device)
+        # models: same construction order as the reference (gcbf.py:87-100) => same seeded initialisation
+        self.cbf = CBFGNN(num_agents=num_agents, node_dim=node_dim, edge_dim=edge_dim, phi_dim=256).to(device)
+        self.actor = GNNController(num_agents=num_agents, node_dim=node_dim, edge_dim=edge_dim, phi_dim=256,
+                                   action_dim=action_dim).to(device)
+        self.lr_cbf, self.lr_actor = 3e-4, 1e-3            # gcbf.py:102-103
+        self.max_grad_norm = 1e-3                          # gcbf.py:223-224
+        self._bucket: Optional[_FlatBucket] = None
+        self.buffer = Buffer()
+        self.memory = Buffer()
+        self.batch_size = batch_size
+        self.params = params if params is not None else {
+            'alpha': 1.0, 'eps': 0.02, 'inner_iter': 10, 'loss_action_coef': 0.001, 'loss_unsafe_coef': 1.,
+            'loss_safe_coef': 1., 'loss_h_dot_coef': 0.1}
+        self.process_group = None   # set to a torch.distributed group for data-parallel training
+
+    # ---- rollout-time API ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def act(self, data) -> Tensor:
+        return self.actor(data)
+
+    @torch.no_grad()
+    def step(self, data, prob: float) -> Tensor:
+        action = self.actor(data)
+        if np.random.rand() < prob:
+            action = torch.zeros_like(action)
+        is_safe = not bool(torch.any(self._env.unsafe_mask(data)))
+        self.buffer.append(data, is_safe)
+        return action
+
+    def is_update(self, step: int) -> bool:
+        return step % self.batch_size == 0
+
+    # ---- the train step -----------------------------------------------------------------------------
+    def _ensure_bucket(self) -> _FlatBucket:
+        if self._bucket is None:
+            self._bucket = _FlatBucket([self.cbf, self.actor], self.device)
+        return self._bucket
+
+    def _world(self):
+        import torch.distributed as dist
+        if self.process_group is None and not (dist.is_available() and dist.is_initialized()):
+            return None, 1
+        return dist, dist.get_world_size(self.process_group)
+
+    def train_step(self, graphs, apply_optim: bool = True, compute_acc_h_dot: bool = True) -> Dict[str, Tensor]:
+        """One inner iteration of GCBF.update (gcbf.py:158-226) on a collated batch.  Returns device tensors
+        (no host sync): 'scalars' = [loss_unsafe, loss_safe, loss_h_dot, loss_action, acc_unsafe, acc_safe,
+        total_loss, num_agents], 'acc_h_dot', plus h / actions / h_next / h_next_new for inspection."""
+        env, hp = self._env, self.params
+        bucket = self._ensure_bucket()
+        dev = graphs.states.device
+        dist, world = self._world()
+        M = graphs.u_ref.shape[0]
+        a_dim = self.action_dim
+
+        h = self.cbf(graphs)                                             # gcbf.py:161  (power iteration #1)
+        actions = self.actor(graphs)                                     # gcbf.py:162
+        masks = env._masks(graphs)                                       # gcbf.py:168, 180 -- one launch
+        graphs_next = env.forward_graph(graphs, actions)                 # gcbf.py:193
+        h_next = self.cbf(graphs_next)                                   # gcbf.py:194  (power iteration #2)
+        with torch.no_grad():                                            # gcbf.py:195-201, batched
+            st_relink = env.next_states_single(graphs, actions)
+            relinked = env.add_communication_links(env.make_graph(st_relink))
+            h_next_new = self.cbf(relinked)                              # power iteration #3, value only
+
+        partial = torch.empty(16, device=dev, dtype=torch.float64)
+        hdot = torch.empty(M, device=dev, dtype=torch.float32)
+        hd, hnd, hnnd, actd = h.detach(), h_next.detach(), h_next_new, actions.detach()
+        safe_u8, unsafe_u8 = masks[0].view(torch.uint8), masks[1].view(torch.uint8)
+        dt = float(env.dt)
+        _C.call('gcbf_loss_partials', _C.ptr(hd), _C.ptr(hnd), _C.ptr(hnnd), _C.ptr(actd), a_dim, _C.ptr(safe_u8),
+                _C.ptr(unsafe_u8), M, float(hp['alpha']), float(hp['eps']), dt, _C.ptr(partial), _C.ptr(hdot))
+        if world > 1:
+            dist.all_reduce(partial, group=self.process_group)           # global counts => global masked means
+        d_h = torch.empty_like(hd)
+        d_hn = torch.empty_like(hnd)
+        d_act = torch.empty_like(actd)
+        scalars = torch.empty(8, device=dev, dtype=torch.float32)
+        _C.call('gcbf_loss_grads', _C.ptr(hd), _C.ptr(hnd), _C.ptr(hnnd), _C.ptr(actd), a_dim, _C.ptr(safe_u8),
+                _C.ptr(unsafe_u8), M, float(hp['alpha']), float(hp['eps']), dt, float(hp['loss_unsafe_coef']),
+                float(hp['loss_safe_coef']), float(hp['loss_h_dot_coef']), float(hp['loss_action_coef']),
+                _C.ptr(partial), _C.ptr(d_h), _C.ptr(d_hn), _C.ptr(d_act), _C.ptr(scalars))
+
+        bucket.zero_grad()                                               # gcbf.py:220-221
+        torch.autograd.backward([h, h_next, actions], [d_h, d_hn, d_act])  # gcbf.py:222
+
+        out = dict(scalars=scalars, h=hd, actions=actd, h_next=hnd, h_next_new=hnnd, safe_mask=masks[0],
+                   unsafe_mask=masks[1], edge_index_new=relinked.edge_index, hdot=hdot)
+        if compute_acc_h_dot:                                            # gcbf.py:209 (M x M broadcast mean)
+            cnt = torch.empty(1, device=dev, dtype=torch.int64)
+            if world > 1:
+                hdot_all = torch.empty(world * M, device=dev, dtype=torch.float32)
+                dist.all_gather_into_tensor(hdot_all, hdot, group=self.process_group)
+            else:
+                hdot_all = hdot
+            _C.call('gcbf_pair_count', _C.ptr(hdot_all), hdot_all.numel(), _C.ptr(hd), M, float(hp['alpha']), _C.ptr(cnt))
+            if world > 1:
+                dist.all_reduce(cnt, group=self.process_group)
+            out['acc_h_dot'] = cnt.to(torch.float64) / float(world * M) / float(world * M)
+
+        if world > 1:
+            dist.all_reduce(bucket.grad, group=self.process_group)       # the ONE gradient collective (K9)
+        if apply_optim:
+            self.optim_step()
+        return out
+
+    def optim_step(self):
+        """clip_grad_norm_(1e-3) per net + Adam (gcbf.py:223-226), fused, on the flat bucket."""
+        b = self._ensure_bucket()
+        b.step += 1
+        b.sumsq.zero_()
+        for i, lr in enumerate((self.lr_cbf, self.lr_actor)):
+            lo, hi = b.ranges[i]
+            g = b.grad[lo:hi]
+            _C.call('gcbf_grad_sumsq', _C.ptr(g), hi - lo, _C.ptr(b.sumsq[i:i + 1]))
+            _C.call('gcbf_clip_adam', _C.ptr(b.flat[lo:hi]), _C.ptr(g), _C.ptr(b.exp_avg[lo:hi]),
+                    _C.ptr(b.exp_avg_sq[lo:hi]), hi - lo, _C.ptr(b.sumsq[i:i + 1]), self.max_grad_norm, lr, 0.9, 0.999,
+                    1e-8, b.step)
+
+    def update(self, step: int, writer=None) -> dict:
+        """Reference-shaped update loop (gcbf.py:144-247): sample segments, collate, `inner_iter` train steps."""
+        seg_len = 3
+        info = {}
+        for i_inner in range(self.params['inner_iter']):
+            if self.memory.size == 0:
+                graph_list = self.buffer.sample(self.batch_size // 5, seg_len)
+            else:
+                graph_list = (self.buffer.sample(self.batch_size // 10, seg_len, True) +
+                              self.memory.sample(self.batch_size // 5 - self.batch_size // 10, seg_len, True))
+            res = self.train_step(Batch.from_data_list(graph_list))
+            s = res['scalars'].tolist()                                  # the one host sync per inner iteration
+            info = {'acc/safe': s[5], 'acc/unsafe': s[4], 'acc/derivative': float(res['acc_h_dot'])}
+            if writer is not None:
+                it = step * self.params['inner_iter'] + i_inner
+                for tag, val in (('loss/unsafe', s[0]), ('loss/safe', s[1]), ('loss/derivative', s[2]),
+                                 ('loss/action', s[3]), ('acc/unsafe', s[4]), ('acc/safe', s[5]),
+                                 ('acc/derivative', info['acc/derivative'])):
+                    writer.add_scalar(tag, val, it)
+        self.memory.merge(self.buffer)
+        self.buffer.clear()
+        return info
+
+    # ---- checkpoints (file names and keys of gcbf.py:249-258) ------------------------------------------
+    def save(self, save_dir: str):
+        os.makedirs(save_dir, exist_ok=True)
+        torch.save(self.cbf.state_dict(), os.path.join(save_dir, 'cbf.pkl'))
+        torch.save(self.actor.state_dict(), os.path.join(save_dir, 'actor.pkl'))
+
+    def load(self, load_dir: str):
+        assert os.path.exists(load_dir)
+        self.cbf.load_state_dict(torch.load(os.path.join(load_dir, 'cbf.pkl'), map_location=self.device))
+        self.actor.load_state_dict(torch.load(os.path.join(load_dir, 'actor.pkl'), map_location=self.device))

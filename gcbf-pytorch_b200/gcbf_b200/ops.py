@@ -1,0 +1,424 @@
+"""Host-side orchestration of the sm_100a kernels: raw op wrappers (one C-ABI call each) and the two
+autograd.Functions the nn.Modules are built from.
+
+    GNNNetFunction   edge-MLP phi -> attention aggregation -> node-MLP gamma [-> row select -> head MLP]
+                     = CBFGNNLayer / ControllerGNNLayer (reference gcbf/nn/gnn.py:14-36, 56-73), optionally fused
+                     with CBFGNN.forward / GNNController.forward (gcbf/algo/gcbf.py:37-55,
+                     gcbf/controller/gnn_controller.py:29-48)
+    MLPFunction      gcbf.nn.MLP.forward (gcbf/nn/mlp.py:44-47)
+
+torch is used for device memory (torch.empty / zeros), streams and autograd bookkeeping only; every
+arithmetic step is a kernel of libgcbf_b200.so.  No CPU fallback: CPU tensors raise.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _C
+from ._C import call, ptr
+
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+ENV_IDS = {'SimpleCar': 0, 'DubinsCar': 1, 'SimpleDrone': 2}
+GEMM_IMPL = 0   # 0 auto, 1 force fp32 SIMT, 2 force tcgen05 (tests flip this)
+
+
+def _mat(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    """2-D fp32 row-major view with unit inner stride; returns (tensor_keeping_storage_alive, ld)."""
+    if t.dim() == 1:
+        t = t.unsqueeze(1)
+    if t.dtype != torch.float32:
+        raise TypeError(f'expected float32, got {t.dtype}')
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    return t, ld
+
+
+# ----------------------------------------------------------------------------------------------------
+# raw ops (each = one C-ABI entry point)
+# ----------------------------------------------------------------------------------------------------
+def linear_fwd(x, W, b, inv_sigma, act, out=None):
+    x, ldx = _mat(x)
+    W, ldw = _mat(W)
+    M, K = x.shape
+    N = W.shape[0]
+    assert W.shape[1] == K, (x.shape, W.shape)
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    y, ldy = _mat(out)
+    assert y.data_ptr() == out.data_ptr()
+    call('gcbf_linear_fwd', ptr(x), ldx, ptr(W), ldw, ptr(b), ptr(inv_sigma), ptr(y), ldy, M, N, K, act, GEMM_IMPL)
+    return out
+
+
+def linear_bwd_data(dz, W, inv_sigma, relu_src, out=None, accumulate=False):
+    dz, lddz = _mat(dz)
+    W, ldw = _mat(W)
+    M, N = dz.shape
+    K = W.shape[1]
+    assert W.shape[0] == N
+    if out is None:
+        assert not accumulate
+        out = torch.empty(M, K, device=dz.device, dtype=torch.float32)
+    o, ldo = _mat(out)
+    assert o.data_ptr() == out.data_ptr()
+    rs, ldr = (None, 0)
+    if relu_src is not None:
+        rs, ldr = _mat(relu_src)
+    call('gcbf_linear_bwd_data', ptr(dz), lddz, ptr(W), ldw, ptr(inv_sigma), ptr(rs), ldr, ptr(o), ldo, M, N, K,
+         1 if accumulate else 0, GEMM_IMPL)
+    return out
+
+
+def linear_bwd_weight(dz, x, inv_sigma, need_bias=True):
+    dz, lddz = _mat(dz)
+    x, ldx = _mat(x)
+    M, N = dz.shape
+    K = x.shape[1]
+    dW = torch.empty(N, K, device=dz.device, dtype=torch.float32)
+    db = torch.empty(N, device=dz.device, dtype=torch.float32) if need_bias else None
+    call('gcbf_linear_bwd_weight', ptr(dz), lddz, ptr(x), ldx, ptr(inv_sigma), ptr(dW), K, ptr(db), M, N, K, 0, GEMM_IMPL)
+    return dW, db
+
+
+def act_bwd(dy, y, act):
+    dy = dy.contiguous()
+    y = y.contiguous()
+    out = torch.empty_like(dy)
+    call('gcbf_act_bwd', ptr(dy), ptr(y), ptr(out), dy.numel(), act)
+    return out
+
+
+_SN_WS = {}
+
+
+def _sn_workspace(device, N, K):
+    need = int(_C.lib().gcbf_sn_workspace_floats(N, K))
+    ws = _SN_WS.get(device)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 16), device=device, dtype=torch.float32)
+        _SN_WS[device] = ws
+    return ws
+
+
+def sn_power_iter(W, u, v):
+    """In-place power iteration on the module buffers u, v; returns the device scalar 1/sigma."""
+    Wm, ldw = _mat(W)
+    N, K = Wm.shape
+    inv_sigma = torch.empty(1, device=W.device, dtype=torch.float32)
+    call('gcbf_sn_power_iter', ptr(Wm), ldw, N, K, ptr(u), ptr(v), ptr(inv_sigma), ptr(_sn_workspace(W.device, N, K)))
+    return inv_sigma
+
+
+def sn_grad_fixup(dW, W, u, v, inv_sigma):
+    Wm, ldw = _mat(W)
+    N, K = Wm.shape
+    call('gcbf_sn_grad_fixup', ptr(dW), K, ptr(Wm), ldw, N, K, ptr(u), ptr(v), ptr(inv_sigma),
+         ptr(_sn_workspace(W.device, N, K)))
+    return dW
+
+
+def copy2d(src, dst, rows, cols):
+    s, lds = _mat(src)
+    d, ldd = _mat(dst)
+    assert d.data_ptr() == dst.data_ptr()
+    call('gcbf_copy2d', ptr(s), lds, ptr(d), ldd, rows, cols)
+
+
+def rows_gather(src, idx, out):
+    s, lds = _mat(src)
+    o, ldo = _mat(out)
+    assert o.data_ptr() == out.data_ptr()
+    call('gcbf_rows_gather', ptr(s), lds, ptr(idx), ptr(o), ldo, idx.numel(), out.shape[1])
+    return out
+
+
+def rows_scatter(src, idx, out):
+    s, lds = _mat(src)
+    o, ldo = _mat(out)
+    assert o.data_ptr() == out.data_ptr()
+    call('gcbf_rows_scatter', ptr(s), lds, ptr(idx), ptr(o), ldo, idx.numel(), src.shape[1])
+    return out
+
+
+def rowptr_from_edge_index(edge_index: torch.Tensor, num_nodes: int, check_sorted: bool = True) -> torch.Tensor:
+    """CSR row pointer (int32, num_nodes+1) over target nodes of a target-sorted edge_index."""
+    _C.require_cuda(edge_index)
+    ei = edge_index.contiguous()
+    E = ei.shape[1]
+    rowptr = torch.empty(num_nodes + 1, device=ei.device, dtype=torch.int32)
+    flag = torch.empty(1, device=ei.device, dtype=torch.int32)
+    dst = ei[1]
+    call('gcbf_rowptr_from_targets', dst.data_ptr() if E else None, E, num_nodes, ptr(rowptr), ptr(flag))
+    if check_sorted and int(flag.item()) != 0:
+        raise ValueError('edge_index[1] (targets) must be in range and sorted ascending: every reference call site '
+                         '(RadiusGraph / nonzero / Batch.from_data_list) produces target-sorted edges')
+    return rowptr
+
+
+def radius_graph(states: torch.Tensor, pos_dim: int, num_graphs: int, nodes_per_graph: int, num_agents: int,
+                 radius: float, metric: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1: returns (edge_index int64 [2,E] sorted (target, source), rowptr int32 over agents)."""
+    _C.require_cuda(states)
+    st, ld = _mat(states)
+    na = num_graphs * num_agents
+    rowptr = torch.empty(na + 1, device=st.device, dtype=torch.int32)
+    call('gcbf_radius_graph_count', ptr(st), ld, pos_dim, num_graphs, nodes_per_graph, num_agents, float(radius),
+         metric, ptr(rowptr))
+    E = int(rowptr[-1].item())          # the one host sync: output size is data dependent
+    ei = torch.empty(2, E, device=st.device, dtype=torch.int64)
+    call('gcbf_radius_graph_fill', ptr(st), ld, pos_dim, num_graphs, nodes_per_graph, num_agents, float(radius),
+         metric, ptr(rowptr), ptr(ei) if E else None, E)
+    return ei, rowptr
+
+
+def edge_attr_fwd(env_id: int, states, edge_index):
+    st, ld = _mat(states)
+    ei = edge_index.contiguous()
+    E = ei.shape[1]
+    ed = {0: 4, 1: 5, 2: 6}[env_id]
+    out = torch.empty(E, ed, device=st.device, dtype=torch.float32)
+    call('gcbf_edge_attr_fwd', env_id, ptr(st), ld, ptr(ei) if E else None, E, ptr(out) if E else None)
+    return out
+
+
+def edge_attr_bwd(env_id: int, states, edge_index, d_edge_attr):
+    st, ld = _mat(states)
+    ei = edge_index.contiguous()
+    E = ei.shape[1]
+    d_states = torch.zeros(st.shape[0], ld, device=st.device, dtype=torch.float32)
+    d_ea = d_edge_attr.contiguous()
+    call('gcbf_edge_attr_bwd', env_id, ptr(st), ld, ptr(ei) if E else None, E, ptr(d_ea) if E else None, ptr(d_states))
+    return d_states[:, :st.shape[1]]
+
+
+class EdgeAttrFunction(torch.autograd.Function):
+    """env.edge_attr(state, edge_index): reference simple_car.py:246-247, dubins_car.py:724-728,
+    simple_drone.py:313-314."""
+
+    @staticmethod
+    def forward(ctx, states, edge_index, env_id):
+        _C.require_cuda(states, edge_index)
+        ctx.env_id = env_id
+        ctx.save_for_backward(states, edge_index)
+        return edge_attr_fwd(env_id, states, edge_index)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        states, edge_index = ctx.saved_tensors
+        return edge_attr_bwd(ctx.env_id, states, edge_index, d_out), None, None
+
+
+# ----------------------------------------------------------------------------------------------------
+# MLP chain
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class LinearSpec:
+    W: torch.Tensor                      # [N, K]  (weight, or weight_orig when spectral-normalised)
+    b: torch.Tensor                      # [N]
+    u: Optional[torch.Tensor] = None     # spectral-norm buffers (updated in place on every forward)
+    v: Optional[torch.Tensor] = None
+    act: int = ACT_NONE
+
+    @property
+    def sn(self) -> bool:
+        return self.u is not None
+
+
+@dataclass
+class MLPCtx:
+    acts: List[torch.Tensor] = field(default_factory=list)      # acts[0] = input, acts[l] = output of layer l
+    inv_sigma: List[Optional[torch.Tensor]] = field(default_factory=list)
+    uv: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = field(default_factory=list)
+
+
+def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool) -> Tuple[torch.Tensor, Optional[MLPCtx]]:
+    ctx = MLPCtx() if save else None
+    if save:
+        ctx.acts.append(x)
+    for L in layers:
+        inv_sigma = None
+        if L.sn:
+            # old-style torch spectral_norm in training mode: one power iteration per forward, even under
+            # no_grad (the reference never calls .eval())
+            inv_sigma = sn_power_iter(L.W, L.u, L.v)
+        x = linear_fwd(x, L.W, L.b, inv_sigma, L.act)
+        if save:
+            ctx.acts.append(x)
+            ctx.inv_sigma.append(inv_sigma)
+            ctx.uv.append((L.u.clone(), L.v.clone()) if L.sn else None)
+    return x, ctx
+
+
+def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, need_dx: bool,
+                 dx_out: Optional[torch.Tensor] = None, dx_accumulate: bool = False):
+    """Returns (dx or None, [(dW, db) per layer])."""
+    grads = [None] * len(layers)
+    dz = dy
+    last = len(layers) - 1
+    if layers[last].act == ACT_TANH:
+        dz = act_bwd(dz, ctx.acts[last + 1], ACT_TANH)
+    elif layers[last].act == ACT_RELU:
+        dz = act_bwd(dz, ctx.acts[last + 1], ACT_RELU)
+    for l in range(last, -1, -1):
+        L = layers[l]
+        x_in = ctx.acts[l]
+        inv_sigma = ctx.inv_sigma[l]
+        dW, db = linear_bwd_weight(dz, x_in, inv_sigma)
+        if L.sn:
+            u, v = ctx.uv[l]
+            sn_grad_fixup(dW, L.W, u, v, inv_sigma)
+        grads[l] = (dW, db)
+        if l > 0:
+            # hidden ReLU of layer l-1 folded into the epilogue: dz_{l-1} = (dz_l W_l) * (y_{l-1} > 0)
+            assert layers[l - 1].act == ACT_RELU
+            dz = linear_bwd_data(dz, L.W, inv_sigma, x_in)
+        elif need_dx:
+            dz = linear_bwd_data(dz, L.W, inv_sigma, None, out=dx_out, accumulate=dx_accumulate)
+        else:
+            dz = None
+    return dz, grads
+
+
+def _flatten_specs(specs: Sequence[LinearSpec]) -> List[torch.Tensor]:
+    out = []
+    for s in specs:
+        out += [s.W, s.b]
+    return out
+
+
+class MLPFunction(torch.autograd.Function):
+    """gcbf.nn.MLP.forward.  apply(x, layers, *flat_params) where flat_params = [W0, b0, W1, b1, ...]."""
+
+    @staticmethod
+    def forward(ctx, x, layers, *params):
+        _C.require_cuda(x)
+        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        y, mctx = mlp_forward(x.detach(), layers, need)
+        ctx.layers, ctx.mctx = layers, mctx
+        ctx.need_dx = x.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx, grads = mlp_backward(ctx.mctx, ctx.layers, dy, ctx.need_dx)
+        flat = []
+        for dW, db in grads:
+            flat += [dW, db]
+        return (dx, None, *flat)
+
+
+# ----------------------------------------------------------------------------------------------------
+# GNN layer (+ optional fused head)
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class NetSpec:
+    phi: List[LinearSpec]
+    gate: List[LinearSpec]
+    gamma: List[LinearSpec]
+    head: Optional[List[LinearSpec]] = None
+    node_dim: int = 4
+    edge_dim: int = 4
+    phi_dim: int = 256
+
+    def all_layers(self):
+        return self.phi + self.gate + self.gamma + (self.head or [])
+
+
+def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head_extra, save):
+    """phi -> attention aggregation -> gamma (on `row_index` rows only when given) -> head.
+    Returns (out, ctx-tuple)."""
+    dev = x.device
+    E = edge_index.shape[1]
+    Nn = x.shape[0]
+    kin = 2 * spec.node_dim + spec.edge_dim
+    ei = edge_index.contiguous()
+    xc = x.contiguous()
+    ea = edge_attr.contiguous()
+    ein = torch.empty(E, kin, device=dev, dtype=torch.float32)
+    call('gcbf_edge_input_fwd', ptr(xc), spec.node_dim, ptr(ea) if E else None, spec.edge_dim, ptr(ei) if E else None,
+         E, ptr(ein) if E else None, kin)
+    msg, c_phi = mlp_forward(ein, spec.phi, save)                        # gnn.py:30-32
+    gate, c_gate = mlp_forward(msg, spec.gate, save)                     # AttentionalAggregation.gate_nn
+    C = spec.phi_dim
+    gin_all = torch.empty(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
+    att = torch.empty(E, device=dev, dtype=torch.float32)
+    call('gcbf_attn_aggr_fwd', ptr(msg) if E else None, C, ptr(gate) if E else None, ptr(rowptr), Nn, C,
+         ptr(att) if E else None, ptr(gin_all), C + spec.node_dim)
+    copy2d(xc, gin_all[:, C:], Nn, spec.node_dim)                        # cat([aggr_out, x])  gnn.py:35
+    if row_index is not None:
+        gin = torch.empty(row_index.numel(), C + spec.node_dim, device=dev, dtype=torch.float32)
+        rows_gather(gin_all, row_index, gin)
+    else:
+        gin = gin_all
+    feat, c_gamma = mlp_forward(gin, spec.gamma, save)                   # gnn.py:34-36
+    c_head = None
+    out = feat
+    hin = None
+    if spec.head is not None:
+        if head_extra is not None:                                       # cat([x, data.u_ref])  gnn_controller.py:46
+            R, F = feat.shape
+            hin = torch.empty(R, F + head_extra.shape[1], device=dev, dtype=torch.float32)
+            copy2d(feat, hin, R, F)
+            copy2d(head_extra.contiguous(), hin[:, F:], R, head_extra.shape[1])
+        else:
+            hin = feat
+        out, c_head = mlp_forward(hin, spec.head, save)
+    ctx = (c_phi, c_gate, c_gamma, c_head, msg, att, Nn, E) if save else None
+    return out, ctx
+
+
+def net_backward(spec: NetSpec, ctx, d_out, rowptr, row_index, need_d_edge_attr):
+    c_phi, c_gate, c_gamma, c_head, msg, att, Nn, E = ctx
+    dev = d_out.device
+    C = spec.phi_dim
+    g_head = []
+    d_feat = d_out
+    if spec.head is not None:
+        d_hin, g_head = mlp_backward(c_head, spec.head, d_out, True)
+        F = spec.gamma[-1].W.shape[0]
+        d_feat = d_hin[:, :F] if d_hin.shape[1] != F else d_hin           # strided view: kernels take ld
+    d_gin, g_gamma = mlp_backward(c_gamma, spec.gamma, d_feat, True)
+    if row_index is not None:
+        d_gin_all = torch.zeros(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
+        rows_scatter(d_gin, row_index, d_gin_all)
+    else:
+        d_gin_all = d_gin
+    d_msg = torch.empty(E, C, device=dev, dtype=torch.float32)
+    d_gate = torch.empty(E, 1, device=dev, dtype=torch.float32)
+    call('gcbf_attn_aggr_bwd', ptr(msg) if E else None, C, ptr(att) if E else None, ptr(rowptr), Nn, C, ptr(d_gin_all),
+         C + spec.node_dim, ptr(d_msg) if E else None, C, ptr(d_gate) if E else None, 0)
+    # gate MLP backward; its input gradient is accumulated onto the aggregation's d_msg
+    _, g_gate = mlp_backward(c_gate, spec.gate, d_gate, True, dx_out=d_msg, dx_accumulate=True)
+    d_ein, g_phi = mlp_backward(c_phi, spec.phi, d_msg, need_d_edge_attr)
+    d_edge_attr = None
+    if need_d_edge_attr:
+        d_edge_attr = d_ein[:, 2 * spec.node_dim:]
+    return d_edge_attr, g_phi + g_gate + g_gamma + g_head
+
+
+class GNNNetFunction(torch.autograd.Function):
+    """apply(x, edge_attr, edge_index, rowptr, row_index, head_extra, spec, *flat_params)."""
+
+    @staticmethod
+    def forward(ctx, x, edge_attr, edge_index, rowptr, row_index, head_extra, spec, *params):
+        _C.require_cuda(x, edge_attr, edge_index)
+        if x.requires_grad:
+            raise NotImplementedError('gradient w.r.t. node features x is not part of the reference hot path '
+                                      '(x is a constant type indicator, simple_car.py:132)')
+        need = torch.is_grad_enabled() and (edge_attr.requires_grad or any(p.requires_grad for p in params))
+        he = head_extra.detach() if head_extra is not None else None
+        out, nctx = net_forward(spec, x.detach(), edge_attr.detach(), edge_index, rowptr, row_index, he, need)
+        ctx.spec, ctx.nctx = spec, nctx
+        ctx.rowptr, ctx.row_index = rowptr, row_index
+        ctx.need_dea = edge_attr.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        d_ea, grads = net_backward(ctx.spec, ctx.nctx, d_out.contiguous(), ctx.rowptr, ctx.row_index, ctx.need_dea)
+        flat = []
+        for dW, db in grads:
+            flat += [dW, db]
+        return (None, d_ea, None, None, None, None, None, *flat)

@@ -1,0 +1,221 @@
+/*
+ * gcbf_b200.h -- C ABI of libgcbf_b200.so: the B200 (sm_100a) hot path of MIT-REALM/gcbf-pytorch.
+ *
+ * The reference has no FFI of its own (it is pure Python on torch / torch_geometric); the boundary a
+ * maintainer binds is therefore the set of tensor operations its Python classes perform.  Every entry
+ * below names the reference site (file:line, relative to the reference checkout) it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - all matrices are dense row-major fp32 with an explicit leading dimension (`ld*`, in elements);
+ *     edge_index is int64 [2, E] (row 0 = source j, row 1 = target i), masks are uint8;
+ *   - nothing here allocates or synchronises: outputs / workspaces are caller-provided, every launch
+ *     goes to `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, negative GCBF_E_* on failure; gcbf_last_error() gives the text;
+ *   - thread-compatible: no global mutable state except the per-thread last-error string.
+ */
+#ifndef GCBF_B200_H
+#define GCBF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCBF_OK 0
+#define GCBF_E_INVALID (-1) /* bad argument (null pointer, negative size, unsupported enum) */
+#define GCBF_E_CUDA (-2)    /* a CUDA runtime call / launch failed */
+#define GCBF_E_UNSUPPORTED (-3)
+
+/* environment kinds: gcbf/env/__init__.py:11-26 */
+#define GCBF_ENV_SIMPLE_CAR 0   /* gcbf/env/simple_car.py  : state [x,y,vx,vy],       edge_dim 4, action 2 */
+#define GCBF_ENV_DUBINS_CAR 1   /* gcbf/env/dubins_car.py  : state [x,y,theta,v],     edge_dim 5, action 2 */
+#define GCBF_ENV_SIMPLE_DRONE 2 /* gcbf/env/simple_drone.py: state [x,y,z,vx,vy,vz], edge_dim 6, action 3 */
+
+/* activation codes for the linear epilogue: gcbf/nn/mlp.py:44-47 (ReLU hidden), gcbf/algo/gcbf.py:34 (Tanh) */
+#define GCBF_ACT_NONE 0
+#define GCBF_ACT_RELU 1
+#define GCBF_ACT_TANH 2
+
+const char* gcbf_last_error(void);
+int gcbf_abi_version(void);
+/* 1 if the library was built with the tcgen05 (3xTF32) GEMM path compiled in, else 0 */
+int gcbf_has_tcgen05(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K1  radius graph.  Replaces SimpleCar.add_communication_links -> torch_cluster.radius_graph
+ * (gcbf/env/simple_car.py:32-33, 249-252; metric 0: sum_d (dx_d)^2 < r*r, unfused) and the dense
+ * torch.norm / nonzero build of DubinsCar / SimpleDrone (gcbf/env/dubins_car.py:730-746,
+ * gcbf/env/simple_drone.py:316-333; metric 1: sqrt(fma-chain) < r, matching torch.norm on CPU).
+ * A batch is `num_graphs` graphs of `nodes_per_graph` rows each, agents first; targets are the first
+ * `num_agents` rows of every graph, sources all rows (SimpleCar: pass nodes_per_graph == num_agents).
+ * `count` writes rowptr[num_graphs*num_agents + 1] (int32 exclusive scan, agent-major); rowptr[last]
+ * is E.  `fill` writes edge_index[2,E] int64 sorted (target asc, source asc) with batch node offsets
+ * (what Batch.from_data_list produces, gcbf/algo/gcbf.py:159,200).
+ * ------------------------------------------------------------------------------------------------- */
+int gcbf_radius_graph_count(const float* states, int ld_state, int pos_dim, int num_graphs,
+                            int nodes_per_graph, int num_agents, float radius, int metric,
+                            int32_t* rowptr, void* stream);
+int gcbf_radius_graph_fill(const float* states, int ld_state, int pos_dim, int num_graphs,
+                           int nodes_per_graph, int num_agents, float radius, int metric,
+                           const int32_t* rowptr, int64_t* edge_index, int64_t num_edges, void* stream);
+/* CSR row pointer over ALL nodes from a target-sorted edge_index row (the `index` PyG's
+ * MessagePassing hands to the aggregation, gcbf/nn/gnn.py:28).  unsorted_flag (device int32) is cleared,
+ * then set to 1 if targets are out of range or not non-decreasing (caller must then sort).  rowptr has
+ * num_nodes+1 int32 entries. */
+int gcbf_rowptr_from_targets(const int64_t* edge_dst, int64_t num_edges, int num_nodes, int32_t* rowptr,
+                             int32_t* unsorted_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K2  edge features.  edge_attr = g(s[src]) - g(s[dst]); g = identity (SimpleCar, SimpleDrone:
+ * simple_car.py:246-247, simple_drone.py:313-314) or [x,y,theta,v cos,v sin] (dubins_car.py:724-728).
+ * bwd accumulates (atomicAdd) into d_states, which the caller zero-initialises.
+ * edge_input builds cat([x_i, x_j, edge_attr]) (gnn.py:31, :68) into rows of leading dim ld_out,
+ * zero-filling the columns past 2*node_dim+edge_dim.
+ * ------------------------------------------------------------------------------------------------- */
+int gcbf_edge_attr_fwd(int env, const float* states, int ld_state, const int64_t* edge_index,
+                       int64_t num_edges, float* edge_attr, void* stream);
+int gcbf_edge_attr_bwd(int env, const float* states, int ld_state, const int64_t* edge_index,
+                       int64_t num_edges, const float* d_edge_attr, float* d_states, void* stream);
+int gcbf_edge_input_fwd(const float* x, int node_dim, const float* edge_attr, int edge_dim,
+                        const int64_t* edge_index, int64_t num_edges, float* out, int ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K3  linear layers of gcbf.nn.MLP (gcbf/nn/mlp.py:44-47).  inv_sigma is a device scalar (1/sigma of
+ * the spectral-normalised layer, mlp.py:21,33) or NULL for 1.
+ *   fwd       : Y[M,N]  = act(inv_sigma * X[M,K] W[N,K]^T + bias[N])
+ *   bwd_data  : dX[M,K] (+)= inv_sigma * dZ[M,N] W[N,K]   (* (relu_src[M,K] > 0) if relu_src != NULL)
+ *   bwd_weight: dW[N,K] (+)= inv_sigma * dZ[M,N]^T X[M,K] ; db[N] (+)= colsum(dZ)   (db may be NULL)
+ *               accumulate != 0 adds into dW/db, otherwise they are overwritten.
+ * impl: 0 = auto, 1 = fp32 SIMT kernel, 2 = tcgen05 3xTF32 kernel (error if shape unsupported).
+ * ------------------------------------------------------------------------------------------------- */
+int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias,
+                    const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act, int impl,
+                    void* stream);
+int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma,
+                         const float* relu_src, int ld_relu, float* dX, int lddx, int M, int N, int K,
+                         int accumulate, int impl, void* stream);
+int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma,
+                           float* dW, int lddw, float* db, int M, int N, int K, int accumulate, int impl,
+                           void* stream);
+/* dZ = dY * act'(Y) for the output activation (tanh: 1 - Y^2; relu: Y > 0).  In place allowed. */
+int gcbf_act_bwd(const float* dY, const float* Y, float* dZ, int64_t count, int act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K4  attention aggregation = torch_geometric AttentionalAggregation as used at gcbf/nn/gnn.py:17-19,
+ * 59-60: att = softmax over the in-edges of each target (max-shifted, denominator + 1e-16),
+ * aggr_i = sum_e att_e * msg_e (zero for nodes without in-edges).  Edges of node i are the contiguous
+ * range rowptr[i]..rowptr[i+1]; one warp per node, shuffle reductions, no atomics.
+ *   fwd: msg[E,C], gate[E] -> att[E], aggr rows (leading dim ld_aggr, C columns written)
+ *   bwd: d_aggr -> d_msg[E,C] (overwritten, or added to if accumulate != 0), d_gate[E]
+ * ------------------------------------------------------------------------------------------------- */
+int gcbf_attn_aggr_fwd(const float* msg, int ld_msg, const float* gate, const int32_t* rowptr,
+                       int num_nodes, int channels, float* att, float* aggr, int ld_aggr, void* stream);
+int gcbf_attn_aggr_bwd(const float* msg, int ld_msg, const float* att, const int32_t* rowptr,
+                       int num_nodes, int channels, const float* d_aggr, int ld_daggr, float* d_msg,
+                       int ld_dmsg, float* d_gate, int accumulate, void* stream);
+/* row gather / scatter by index: the `x[data.agent_mask]` selection of gcbf/algo/gcbf.py:52-53 and
+ * gcbf/controller/gnn_controller.py:44-45 (idx = nonzero(agent_mask), int64).
+ *   gather : dst[r, 0:cols] = src[idx[r], 0:cols]         r < rows
+ *   scatter: dst[idx[r], 0:cols] = src[r, 0:cols]          (adjoint; caller zero-fills dst, idx unique) */
+int gcbf_rows_gather(const float* src, int ld_src, const int64_t* idx, float* dst, int ld_dst, int64_t rows,
+                     int cols, void* stream);
+int gcbf_rows_scatter(const float* src, int ld_src, const int64_t* idx, float* dst, int ld_dst, int64_t rows,
+                      int cols, void* stream);
+/* strided 2-D copy dst[r, 0:cols] = src[r, 0:cols] (concats such as cat([aggr, x]), cat([feat, u_ref])) */
+int gcbf_copy2d(const float* src, int ld_src, float* dst, int ld_dst, int64_t rows, int cols, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K5  nominal controller + one finite-difference step.
+ *   u_ref : simple_car.py:270-304 (LQR + over-speed penalty), dubins_car.py:764-816 (PID),
+ *           simple_drone.py:349-377.  goal is [num_agents, goal_dim] shared by all graphs; K is the
+ *           LQR gain [action_dim, state_dim] (NULL for DubinsCar).
+ *   step  : forward_graph + MultiAgentEnv.forward + dynamics: x+ = x + dt f(x, clamp(u + u_ref(x)))
+ *           (simple_car.py:178-194,78-89; dubins_car.py:617-635,110-132; simple_drone.py:236-253,103-120;
+ *           gcbf/env/base.py:381-398).  `freeze` != 0 reproduces the single-graph reach-freeze branch.
+ *           pass_mask[num_agents_total, action_dim] (uint8) records where the clamp passes gradient
+ *           (and is 0 for agents frozen by the reach test).
+ *   step_bwd: d_action = (d x+ / d u)^T d_states_next, masked by pass_mask.
+ * ------------------------------------------------------------------------------------------------- */
+/* Environment description shared by K5/K6.  The doubles are the reference's python-float parameters
+ * (`default_params`, simple_car.py:67-76, dubins_car.py:88-100, simple_drone.py:71-82); thresholds such as
+ * 4*car_radius are formed in double and then rounded to fp32 exactly as torch does with python scalars. */
+typedef struct gcbf_env_cfg {
+  int32_t env;             /* GCBF_ENV_* */
+  int32_t num_graphs;      /* B */
+  int32_t nodes_per_graph; /* N = agents + obstacles (agents first) */
+  int32_t num_agents;      /* n */
+  double agent_radius;     /* car_radius / drone_radius */
+  double speed_limit;
+  double dist2goal;
+  double dt;
+} gcbf_env_cfg;
+
+int gcbf_u_ref(const gcbf_env_cfg* cfg, const float* states, int ld_state, const float* goal, int ld_goal,
+               const float* K, float* u_ref, void* stream);
+int gcbf_step_fwd(const gcbf_env_cfg* cfg, const float* states, int ld_state, const float* action,
+                  const float* goal, int ld_goal, const float* K, int freeze, float* states_next,
+                  uint8_t* pass_mask, void* stream);
+int gcbf_step_bwd(const gcbf_env_cfg* cfg, const float* d_states_next, int ld_state,
+                  const uint8_t* pass_mask, float* d_action, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K6  safe / unsafe masks and the CBF losses.
+ *   masks: simple_car.py:306-370, dubins_car.py:818-882, simple_drone.py:379-444 (per-env constants kept).
+ *   loss_partials: local sums for gcbf/algo/gcbf.py:168-212 -> partial[16] (see GCBF_LP_* indices);
+ *                  hdot_out (optional) receives the h_dot values of gcbf.py:202-205.
+ *   loss_grads   : with (possibly all-reduced) partials, d loss / d h, d h_next, d actions of
+ *                  gcbf.py:215-218, and the four loss values + accuracies -> scalars[8].
+ *   pair_count   : number of (i, j) with hdot[j] + alpha*h[i] >= 0 -- the M x M broadcast of gcbf.py:209.
+ * ------------------------------------------------------------------------------------------------- */
+int gcbf_masks(const gcbf_env_cfg* cfg, const float* states, int ld_state, uint8_t* safe, uint8_t* unsafe,
+               uint8_t* collision /* optional: collision_mask, simple_car.py:372-387 */, void* stream);
+#define GCBF_LP_SUM_UNSAFE 0
+#define GCBF_LP_CNT_UNSAFE 1
+#define GCBF_LP_OK_UNSAFE 2
+#define GCBF_LP_SUM_SAFE 3
+#define GCBF_LP_CNT_SAFE 4
+#define GCBF_LP_OK_SAFE 5
+#define GCBF_LP_SUM_HDOT 6
+#define GCBF_LP_CNT_ALL 7
+#define GCBF_LP_SUM_ACT 8
+#define GCBF_LP_SIZE 16
+int gcbf_loss_partials(const float* h, const float* h_next, const float* h_next_new, const float* action,
+                       int action_dim, const uint8_t* safe, const uint8_t* unsafe, int64_t num_agents_total,
+                       float alpha, float eps, float dt, double* partial, float* hdot_out, void* stream);
+int gcbf_loss_grads(const float* h, const float* h_next, const float* h_next_new, const float* action,
+                    int action_dim, const uint8_t* safe, const uint8_t* unsafe, int64_t num_agents_total,
+                    float alpha, float eps, float dt, float coef_unsafe, float coef_safe, float coef_hdot,
+                    float coef_action, const double* partial, float* d_h, float* d_h_next, float* d_action,
+                    float* scalars, void* stream);
+int gcbf_pair_count(const float* hdot, int64_t m_cols, const float* h, int64_t m_rows, float alpha,
+                    unsigned long long* count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K7  spectral norm (old-style torch.nn.utils.spectral_norm, training mode, 1 power iteration,
+ * eps 1e-12; reached from gcbf/nn/mlp.py:21,33 on EVERY forward): v <- normalize(W^T u),
+ * u <- normalize(W v), inv_sigma <- 1 / (u . W v).  u, v updated in place.  workspace: >= (rows_split*K
+ * + N + 8) floats, see gcbf_sn_workspace_floats.
+ *   sn_grad_fixup: given dW = dL/d(W/sigma) / sigma (what bwd_weight produced with inv_sigma), subtract
+ *   the term through sigma: dW -= <dW, W> * inv_sigma * u v^T.
+ * ------------------------------------------------------------------------------------------------- */
+size_t gcbf_sn_workspace_floats(int N, int K);
+int gcbf_sn_power_iter(const float* W, int ldw, int N, int K, float* u, float* v, float* inv_sigma,
+                       float* workspace, void* stream);
+int gcbf_sn_grad_fixup(float* dW, int lddw, const float* W, int ldw, int N, int K, const float* u,
+                       const float* v, const float* inv_sigma, float* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K8  clip_grad_norm_(max_norm) + Adam on one flat parameter bucket (gcbf/algo/gcbf.py:102-103,
+ * 220-226): sumsq[0] += sum g^2 (double);  then p, m, v updated with g * min(1, max_norm/(sqrt(sumsq)+1e-6)).
+ * ------------------------------------------------------------------------------------------------- */
+int gcbf_grad_sumsq(const float* g, int64_t count, double* sumsq, void* stream);
+int gcbf_clip_adam(float* p, const float* g, float* m, float* v, int64_t count, const double* sumsq,
+                   double max_norm, double lr, double beta1, double beta2, double eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCBF_B200_H */

@@ -1,0 +1,133 @@
+"""CPU tests of the host side: C-ABI library loads and exports every symbol include/gcbf_b200.h declares (no
+compute calls without a GPU), graph containers, replay buffer, checkpoint key contract, and that the product
+path refuses to run without CUDA (no silent CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from gcbf_b200 import _C
+from gcbf_b200.data import Batch, Data
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'gcbf_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(gcbf_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert _C.library_available(), 'libgcbf_b200.so missing: run python gcbf-pytorch_b200/csrc/build.py'
+    lib = ctypes.CDLL(_C.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/gcbf_b200.h but not exported'
+    assert sorted(_C.EXPORTED_SYMBOLS) == declared, set(_C.EXPORTED_SYMBOLS) ^ set(declared)
+    assert _C.lib().gcbf_abi_version() == 1
+
+
+def test_env_cfg_struct_layout():
+    assert ctypes.sizeof(_C.EnvCfg) == 4 * 4 + 4 * 8
+
+
+def test_no_cpu_fallback():
+    from gcbf_b200.nn import MLP
+    m = MLP(8, 4, (16,))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(torch.zeros(3, 8))
+
+
+def test_data_semantics():
+    d = Data(x=torch.zeros(3, 4), states=torch.ones(3, 4), edge_attr=None)
+    assert d.edge_attr is None and d.edge_index is None and 'edge_attr' not in d
+    assert not hasattr(d, 'agent_mask') and hasattr(d, 'states')
+    d.update(Data(u_ref=torch.zeros(3, 2)))
+    assert 'u_ref' in d and d.num_nodes == 3
+    d.u_ref = None
+    assert not hasattr(d, 'u_ref')
+
+
+def test_batch_roundtrip():
+    gs = []
+    for k in range(3):
+        n = 4
+        ei = torch.tensor([[1, 2, 0], [0, 0, 3]])
+        gs.append(Data(x=torch.full((n, 4), float(k)), states=torch.rand(n, 4), edge_index=ei,
+                       edge_attr=torch.rand(3, 4), agent_mask=torch.tensor([True, True, False, False])))
+    b = Batch.from_data_list(gs)
+    assert b.num_graphs == 3 and b.num_nodes == 12
+    assert b.edge_index.shape == (2, 9) and torch.equal(b.edge_index[:, 3:6], gs[1].edge_index + 4)
+    assert torch.equal(b.batch, torch.arange(3).repeat_interleave(4)) and b.ptr.tolist() == [0, 4, 8, 12]
+    back = b.to_data_list()
+    for g, r in zip(gs, back):
+        for k in g.keys():
+            assert torch.equal(g[k], r[k]), k
+    assert isinstance(b, Batch) and isinstance(b, Data)
+
+
+def test_buffer_sampling():
+    import numpy as np
+    import random
+    from gcbf_b200.algo.buffer import Buffer
+    np.random.seed(0)
+    random.seed(0)
+    buf = Buffer()
+    for i in range(50):
+        buf.append(i, is_safe=(i % 5 != 0))
+    s = buf.sample(10, 3)
+    assert len(s) == len(set(s)) and s == sorted(s) and len(s) <= 30
+    s2 = buf.sample(10, 3, True)
+    assert len(s2) == len(set(s2))
+    other = Buffer()
+    other.append(100, True)
+    buf.merge(other)
+    assert buf.size == 51 and buf.safe_data[-1] == 50
+    buf.clear()
+    assert buf.size == 0
+
+
+def test_state_dict_key_contract():
+    from gcbf_b200.algo.gcbf import CBFGNN
+    from gcbf_b200.controller import GNNController
+    cbf = CBFGNN(16, 4, 5, 256)
+    keys = list(cbf.state_dict().keys())
+    assert 'feat_transformer.module_0.phi.net.0.weight_orig' in keys
+    assert 'feat_transformer.module_0.phi.net.4.weight_v' in keys
+    assert 'feat_transformer.module_0.aggr_module.gate_nn.net.4.weight' in keys
+    assert 'feat_2_CBF.net.6.bias' in keys and len(keys) == 38
+    assert cbf.state_dict()['feat_transformer.module_0.phi.net.0.weight_orig'].shape == (2048, 13)
+    act = GNNController(16, 4, 5, 256, 2)
+    ak = list(act.state_dict().keys())
+    assert len(ak) == 26 and 'feat_2_action.net.0.weight' in ak
+    assert act.state_dict()['feat_2_action.net.0.weight'].shape == (512, 1026)
+
+
+def test_flat_bucket_views_survive_load_state_dict():
+    from gcbf_b200.algo import make_algo
+    from gcbf_b200.env import make_env
+    dev = torch.device('cpu')
+    env = make_env('SimpleCar', 4, dev)
+    algo = make_algo('gcbf', env, 4, 4, 4, 2, dev)
+    b = algo._ensure_bucket()
+    n_params = sum(p.numel() for p in algo.cbf.parameters()) + sum(p.numel() for p in algo.actor.parameters())
+    assert b.flat.numel() == n_params
+    sd = {k: v.clone() + 1 for k, v in algo.cbf.state_dict().items()}
+    algo.cbf.load_state_dict(sd)
+    p0 = next(algo.cbf.parameters())
+    assert p0.data_ptr() == b.flat.data_ptr() and torch.equal(b.flat[:p0.numel()].view_as(p0), p0)
+    assert p0.grad.data_ptr() == b.grad.data_ptr()
+
+
+def test_dropin_alias():
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from gcbf.nn import MLP, CBFGNNLayer; from gcbf.algo import make_algo; from gcbf.env import make_env;"
+            "from gcbf.controller import GNNController; from gcbf.trainer import Trainer; import gcbf.algo.gcbf as g;"
+            "print(g.GCBF.__module__)") % (os.path.join(ROOT, 'gcbf-pytorch_b200'), os.path.join(ROOT, 'gcbf-pytorch_b200', 'dropin'))
+    out = subprocess.check_output([sys.executable, '-c', code], text=True)
+    assert out.strip() == 'gcbf_b200.algo.gcbf'

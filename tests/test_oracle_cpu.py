@@ -1,0 +1,108 @@
+"""CPU tests of the oracle (oracle/gcbf_oracle.py):
+  1. against the committed golden fixtures (generated from the reference by oracle/make_golden.py);
+  2. against the live reference (oracle/ref_harness.py in a subprocess) when /root/reference is present;
+  3. semantic known-answer on the shipped pretrained checkpoints (when present).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import gcbf_oracle as O
+from conftest import ROOT, digest_close, golden_cases, load_golden
+from helpers import case_inputs, oracle_batch, sd_clone, seeded_algo
+
+REF = '/root/reference'
+has_ref = os.path.isdir(os.path.join(REF, 'gcbf'))
+
+
+def _run_port(fix_like_meta, sb, n_steps):
+    env_name, n = sb.env, sb.num_agents
+    _, algo = seeded_algo(env_name, n, torch.device('cpu'), fix_like_meta['init_seed'],
+                          {'num_obs': sb.num_obs, 'area_size': sb.area_size})
+    cbf, act = sd_clone(algo.cbf), sd_clone(algo.actor)
+    ob = oracle_batch(sb)
+    e_attr = O.edge_attr(env_name, sb.states, ob['edge_index'])
+    import copy
+    with torch.no_grad():
+        h = O.cbf_forward(copy.deepcopy(cbf), ob['x'], e_attr, ob['edge_index'], ob['agent_mask'])
+        u = O.actor_forward(act, ob['x'], e_attr, ob['edge_index'], ob['agent_mask'], ob['u_ref'])
+    oc, oa, steps = {}, {}, []
+    for _ in range(n_steps):
+        steps.append(O.update_step(env_name, cbf, act, oc, oa, sb.states, sb.goals, ob['edge_index'], ob['u_ref'],
+                                   sb.num_graphs, n, sb.num_obs, K=ob['K']))
+    return dict(ob=ob, edge_attr=e_attr, h=h, u=u, steps=steps, cbf=cbf, actor=act, init=(sd_clone(algo.cbf), sd_clone(algo.actor)))
+
+
+@pytest.mark.parametrize('case', golden_cases())
+def test_port_matches_golden(case):
+    fix = load_golden(case)
+    meta = fix['meta']
+    sb = case_inputs(meta)
+    if case.endswith('freeze'):
+        sb.states[0, :2] = sb.goals[0, :2]
+        sb.states[3, :2] = sb.goals[3, :2] + 0.01
+    assert torch.equal(sb.states, fix['states']) and torch.equal(sb.goals, fix['goals'])
+    r = _run_port(meta, sb, meta['steps'])
+    assert not digest_close(r['init'][0], fix['cbf_init'], 0, 0), 'seeded CBF init differs from the reference'
+    assert not digest_close(r['init'][1], fix['actor_init'], 0, 0)
+    assert torch.equal(r['ob']['edge_index'], fix['edge_index'])                      # bit-exact
+    assert torch.equal(r['ob']['u_ref'], fix['u_ref'])
+    assert torch.equal(r['edge_attr'], fix['edge_attr'])
+    assert torch.allclose(r['h'], fix['h_probe'], rtol=0, atol=1e-7)
+    assert torch.allclose(r['u'], fix['u_probe'], rtol=0, atol=1e-6)
+    assert torch.equal(r['steps'][0]['unsafe_mask'], fix['unsafe_mask'])
+    assert torch.equal(r['steps'][0]['safe_mask'], fix['safe_mask'])
+    for st, gold in zip(r['steps'], fix['steps']):
+        for tag, key in (('loss/unsafe', 'loss_unsafe'), ('loss/safe', 'loss_safe'), ('loss/derivative', 'loss_h_dot'),
+                         ('loss/action', 'loss_action'), ('acc/unsafe', 'acc_unsafe'), ('acc/safe', 'acc_safe'),
+                         ('acc/derivative', 'acc_h_dot')):
+            assert abs(float(st[key]) - gold['scalars'][tag]) <= 1e-6, (tag, float(st[key]), gold['scalars'][tag])
+    assert not digest_close(r['cbf'], fix['cbf_final'], 1e-6, 1e-6)
+    assert not digest_close(r['actor'], fix['actor_final'], 1e-6, 1e-6)
+
+
+@pytest.mark.skipif(not has_ref, reason='reference checkout not present (GPU box)')
+@pytest.mark.parametrize('cfg', [('SimpleCar', 12, 0, 2, 2.0), ('DubinsCar', 10, 3, 2, 2.0), ('SimpleDrone', 6, 6, 2, 1.0)])
+def test_port_matches_live_reference(cfg, tmp_path):
+    env_name, n, obs, graphs, area = cfg
+    out = tmp_path / 'ref.pt'
+    subprocess.check_call([sys.executable, os.path.join(ROOT, 'oracle', 'ref_harness.py'), '--env', env_name, '--n', str(n),
+                           '--obs', str(obs), '--graphs', str(graphs), '--area', str(area), '--seed', '5', '--steps', '1',
+                           '--out', str(out)], stderr=subprocess.DEVNULL)
+    ref = torch.load(out, weights_only=False)
+    from gcbf_b200 import synth
+    sb = synth.make_states(env_name, n, obs, graphs, area, 5)
+    r = _run_port(dict(init_seed=0), sb, 1)
+    assert torch.equal(r['ob']['edge_index'], ref['edge_index'])
+    assert torch.equal(r['h'], ref['h_probe']) and torch.equal(r['u'], ref['u_probe'])
+    for k in ref['cbf_final']:
+        assert torch.equal(r['cbf'][k], ref['cbf_final'][k]), k
+    for k in ref['actor_final']:
+        assert torch.equal(r['actor'][k], ref['actor_final'][k]), k
+
+
+@pytest.mark.skipif(not has_ref, reason='pretrained checkpoints live in the reference checkout')
+def test_pretrained_semantic_known_answer():
+    """The shipped SimpleCar CBF must separate colliding from well-separated agents when evaluated through the
+    port's restatement of PyG's message ordering / attention: a wrong gather order or softmax
+    grouping destroys this."""
+    cbf = torch.load(os.path.join(REF, 'pretrained/SimpleCar/models/step_500000/cbf.pkl'), map_location='cpu')
+    from gcbf_b200 import synth
+    hs, safe, coll = [], [], []
+    for seed in range(20):
+        sb = synth.make_states('SimpleCar', 16, 0, 1, 2.0, 100 + seed)
+        sb.states[:, 2:] = 0
+        ob = oracle_batch(sb)
+        ea = O.edge_attr('SimpleCar', sb.states, ob['edge_index'])
+        with torch.no_grad():
+            hs.append(O.cbf_forward(cbf, ob['x'], ea, ob['edge_index'], None).reshape(-1))
+        d = torch.cdist(sb.states[:, :2], sb.states[:, :2]) + torch.eye(16) * 10
+        safe.append(d.min(dim=1)[0] > 0.3)
+        coll.append(d.min(dim=1)[0] < 0.1)
+    h, safe, coll = torch.cat(hs), torch.cat(safe), torch.cat(coll)
+    assert coll.sum() > 5 and safe.sum() > 50
+    assert (h[coll] < 0).float().mean() > 0.9
+    assert (h[safe] >= 0).float().mean() > 0.9
