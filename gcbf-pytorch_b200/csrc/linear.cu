@@ -25,6 +25,9 @@ int launch_tc_wgrad(const float* dZ, int lddz, const float* X, int ldx, const fl
 
 using namespace gcbf;
 
+static thread_local int g_last_impl = 0;
+extern "C" int gcbf_last_gemm_impl(void) { return g_last_impl; }
+
 extern "C" int gcbf_has_tcgen05(void) {
 #ifdef GCBF_WITH_TCGEN05
   return 1;
@@ -42,10 +45,11 @@ extern "C" int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw,
   GCBF_REQUIRE(X && W && Y, "gcbf_linear_fwd: null pointer");
   cudaStream_t st = as_stream(stream);
 #ifdef GCBF_WITH_TCGEN05
-  if (impl != 1 && tc_fwd_supported(ldx, ldw, ldy, M, N, K))
-    return launch_tc_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
+  if (impl != 1 && tc_fwd_supported(ldx, ldw, ldy, M, N, K)) { g_last_impl = 2;
+    return launch_tc_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st); }
 #endif
   if (impl == 2) { set_error("gcbf_linear_fwd: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  g_last_impl = 1;
   return launch_simt_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
 }
 
@@ -58,10 +62,11 @@ extern "C" int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, i
   GCBF_REQUIRE(dZ && W && dX, "gcbf_linear_bwd_data: null pointer");
   cudaStream_t st = as_stream(stream);
 #ifdef GCBF_WITH_TCGEN05
-  if (impl != 1 && tc_dgrad_supported(lddz, ldw, lddx, M, N, K))
-    return launch_tc_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
+  if (impl != 1 && tc_dgrad_supported(lddz, ldw, lddx, M, N, K)) { g_last_impl = 2;
+    return launch_tc_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st); }
 #endif
   if (impl == 2) { set_error("gcbf_linear_bwd_data: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  g_last_impl = 1;
   return launch_simt_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
 }
 
@@ -80,9 +85,10 @@ extern "C" int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X,
   }
   GCBF_REQUIRE(dZ && X, "gcbf_linear_bwd_weight: null pointer");
 #ifdef GCBF_WITH_TCGEN05
-  if (impl != 1 && tc_wgrad_supported(lddz, ldx, lddw, M, N, K))
-    return launch_tc_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);
+  if (impl != 1 && tc_wgrad_supported(lddz, ldx, lddw, M, N, K)) { g_last_impl = 2;
+    return launch_tc_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st); }
 #endif
   if (impl == 2) { set_error("gcbf_linear_bwd_weight: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  g_last_impl = 1;
   return launch_simt_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);
 }

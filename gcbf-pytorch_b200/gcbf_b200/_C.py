@@ -25,6 +25,7 @@ _SIGS = {
     'gcbf_last_error': (c_char_p, []),
     'gcbf_abi_version': (c_int, []),
     'gcbf_has_tcgen05': (c_int, []),
+    'gcbf_last_gemm_impl': (c_int, []),
     'gcbf_radius_graph_count': (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P]),
     'gcbf_radius_graph_fill': (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P, c_int64, P]),
     'gcbf_rowptr_from_targets': (c_int, [P, c_int64, c_int, P, P, P]),
@@ -93,9 +94,24 @@ def check(rc, what):
         raise RuntimeError(f'{what} failed (code {rc}): {msg.decode() if msg else ""}')
 
 
+# kernels launched by one call of each entry point (for bench.py's `gpu_launches`; memsets are not counted)
+_KERNELS_PER_CALL = {'gcbf_radius_graph_count': 2, 'gcbf_sn_power_iter': 4, 'gcbf_sn_grad_fixup': 2, 'gcbf_linear_bwd_weight': 2}
+KERNEL_LAUNCHES = 0
+ABI_CALLS = 0
+
+
+def reset_counters():
+    global KERNEL_LAUNCHES, ABI_CALLS
+    KERNEL_LAUNCHES = 0
+    ABI_CALLS = 0
+
+
 def call(name, *args):
     """Invoke a status-returning entry point on the current CUDA stream and raise on error."""
+    global KERNEL_LAUNCHES, ABI_CALLS
     check(getattr(lib(), name)(*args, stream()), name)
+    ABI_CALLS += 1
+    KERNEL_LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
 
 
 def require_cuda(*tensors):

@@ -93,8 +93,8 @@ class _GNNLayerBase(nn.Module):
         with torch.no_grad():
             E = data.edge_index.shape[1]
             ein = torch.empty(E, 2 * spec.node_dim + spec.edge_dim, device=data.x.device)
-            ops.call('gcbf_edge_input_fwd', ops.ptr(data.x.contiguous()), spec.node_dim,
-                     ops.ptr(data.edge_attr.contiguous()), spec.edge_dim, ops.ptr(data.edge_index.contiguous()), E,
+            xc, eac, eic = data.x.contiguous(), data.edge_attr.contiguous(), data.edge_index.contiguous()
+            ops.call('gcbf_edge_input_fwd', ops.ptr(xc), spec.node_dim, ops.ptr(eac), spec.edge_dim, ops.ptr(eic), E,
                      ops.ptr(ein), ein.shape[1])
             msg, _ = ops.mlp_forward(ein, spec.phi, False)
             gate, _ = ops.mlp_forward(msg, spec.gate, False)

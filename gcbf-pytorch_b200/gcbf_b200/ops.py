@@ -23,6 +23,46 @@ ENV_IDS = {'SimpleCar': 0, 'DubinsCar': 1, 'SimpleDrone': 2}
 GEMM_IMPL = 0   # 0 auto, 1 force fp32 SIMT, 2 force tcgen05 (tests flip this)
 
 
+class _GemmTimer:
+    """Optional CUDA-event timing of every linear-layer launch (bench.py's roofline numbers).  Events are recorded
+    on the launching stream around each C-ABI GEMM call; summary() synchronises and adds them up."""
+
+    def __init__(self):
+        self.on = False
+        self.records = []
+
+    def enable(self):
+        self.on, self.records = True, []
+
+    def disable(self):
+        self.on, self.records = False, []
+
+    def run(self, flops, fn):
+        if not self.on:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.records.append((e0, e1, flops, _C.lib().gcbf_last_gemm_impl()))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        by = {1: [0.0, 0.0, 0], 2: [0.0, 0.0, 0]}
+        for e0, e1, flops, impl in self.records:
+            b = by.get(impl, by[1])
+            b[0] += e0.elapsed_time(e1)
+            b[1] += flops
+            b[2] += 1
+        tensor = by[2][1] > by[1][1]
+        ms, flops, n = by[2] if tensor else by[1]
+        return dict(kernel='gemm_tcgen05_3xtf32' if tensor else 'gemm_simt_kernel', ms=ms, flops=flops, launches=n, tensor=tensor,
+                    other_ms=(by[1] if tensor else by[2])[0], other_flops=(by[1] if tensor else by[2])[1])
+
+
+GEMM_TIMER = _GemmTimer()
+
+
 def _mat(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
     """2-D fp32 row-major view with unit inner stride; returns (tensor_keeping_storage_alive, ld)."""
     if t.dim() == 1:
@@ -48,7 +88,8 @@ def linear_fwd(x, W, b, inv_sigma, act, out=None):
         out = torch.empty(M, N, device=x.device, dtype=torch.float32)
     y, ldy = _mat(out)
     assert y.data_ptr() == out.data_ptr()
-    call('gcbf_linear_fwd', ptr(x), ldx, ptr(W), ldw, ptr(b), ptr(inv_sigma), ptr(y), ldy, M, N, K, act, GEMM_IMPL)
+    GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_fwd', ptr(x), ldx, ptr(W), ldw, ptr(b), ptr(inv_sigma), ptr(y), ldy,
+                                                 M, N, K, act, GEMM_IMPL))
     return out
 
 
@@ -66,8 +107,8 @@ def linear_bwd_data(dz, W, inv_sigma, relu_src, out=None, accumulate=False):
     rs, ldr = (None, 0)
     if relu_src is not None:
         rs, ldr = _mat(relu_src)
-    call('gcbf_linear_bwd_data', ptr(dz), lddz, ptr(W), ldw, ptr(inv_sigma), ptr(rs), ldr, ptr(o), ldo, M, N, K,
-         1 if accumulate else 0, GEMM_IMPL)
+    GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_data', ptr(dz), lddz, ptr(W), ldw, ptr(inv_sigma), ptr(rs), ldr,
+                                                 ptr(o), ldo, M, N, K, 1 if accumulate else 0, GEMM_IMPL))
     return out
 
 
@@ -78,7 +119,8 @@ def linear_bwd_weight(dz, x, inv_sigma, need_bias=True):
     K = x.shape[1]
     dW = torch.empty(N, K, device=dz.device, dtype=torch.float32)
     db = torch.empty(N, device=dz.device, dtype=torch.float32) if need_bias else None
-    call('gcbf_linear_bwd_weight', ptr(dz), lddz, ptr(x), ldx, ptr(inv_sigma), ptr(dW), K, ptr(db), M, N, K, 0, GEMM_IMPL)
+    GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_weight', ptr(dz), lddz, ptr(x), ldx, ptr(inv_sigma), ptr(dW), K,
+                                                 ptr(db), M, N, K, 0, GEMM_IMPL))
     return dW, db
 
 
@@ -294,10 +336,10 @@ class MLPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, layers, *params):
         _C.require_cuda(x)
-        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
         y, mctx = mlp_forward(x.detach(), layers, need)
         ctx.layers, ctx.mctx = layers, mctx
-        ctx.need_dx = x.requires_grad
+        ctx.need_dx = ctx.needs_input_grad[0]
         return y
 
     @staticmethod
@@ -407,12 +449,12 @@ class GNNNetFunction(torch.autograd.Function):
         if x.requires_grad:
             raise NotImplementedError('gradient w.r.t. node features x is not part of the reference hot path '
                                       '(x is a constant type indicator, simple_car.py:132)')
-        need = torch.is_grad_enabled() and (edge_attr.requires_grad or any(p.requires_grad for p in params))
+        need = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
         he = head_extra.detach() if head_extra is not None else None
         out, nctx = net_forward(spec, x.detach(), edge_attr.detach(), edge_index, rowptr, row_index, he, need)
         ctx.spec, ctx.nctx = spec, nctx
         ctx.rowptr, ctx.row_index = rowptr, row_index
-        ctx.need_dea = edge_attr.requires_grad
+        ctx.need_dea = ctx.needs_input_grad[1]
         return out
 
     @staticmethod

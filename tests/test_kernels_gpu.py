@@ -167,10 +167,10 @@ def test_attention_aggregation_fwd_bwd(deg_hi):
     (want * w).sum().backward()
     rowptr = torch.zeros(N + 1, dtype=torch.int32)
     rowptr[1:] = deg.cumsum(0).int()
-    msg_d, gate_d = msg.detach().to(DEV), gate.detach().to(DEV)
+    msg_d, gate_d, rowptr_d = msg.detach().to(DEV), gate.detach().to(DEV), rowptr.to(DEV)
     out = torch.full((N, C + 4), 7.0, device=DEV)
     att_d = torch.empty(E, device=DEV)
-    _C.call('gcbf_attn_aggr_fwd', _C.ptr(msg_d), C, _C.ptr(gate_d), _C.ptr(rowptr.to(DEV)), N, C, _C.ptr(att_d), _C.ptr(out), C + 4)
+    _C.call('gcbf_attn_aggr_fwd', _C.ptr(msg_d), C, _C.ptr(gate_d), _C.ptr(rowptr_d), N, C, _C.ptr(att_d), _C.ptr(out), C + 4)
     assert torch.allclose(out[:, :C].cpu(), want.detach(), rtol=1e-5, atol=1e-5)
     assert (out[:, C:] == 7.0).all()
     assert torch.allclose(att_d.cpu(), att.detach().reshape(-1), rtol=1e-5, atol=1e-6)
@@ -178,7 +178,7 @@ def test_attention_aggregation_fwd_bwd(deg_hi):
     d_gate = torch.empty(E, device=DEV)
     d_aggr = torch.zeros(N, C + 4, device=DEV)
     d_aggr[:, :C] = w.to(DEV)
-    _C.call('gcbf_attn_aggr_bwd', _C.ptr(msg_d), C, _C.ptr(att_d), _C.ptr(rowptr.to(DEV)), N, C, _C.ptr(d_aggr), C + 4,
+    _C.call('gcbf_attn_aggr_bwd', _C.ptr(msg_d), C, _C.ptr(att_d), _C.ptr(rowptr_d), N, C, _C.ptr(d_aggr), C + 4,
             _C.ptr(d_msg), C, _C.ptr(d_gate), 0)
     assert torch.allclose(d_msg.cpu(), msg.grad, rtol=1e-4, atol=1e-5)
     assert torch.allclose(d_gate.cpu(), gate.grad.reshape(-1), rtol=1e-3, atol=2e-5)
@@ -253,14 +253,14 @@ def test_loss_kernels_match_reference_formulas():
     la = torch.square(ar).sum(dim=1).mean()
     (cu * lu + cs * ls + ch * lh + ca * la).backward()
     acc = O.acc_h_dot_broadcast(hd.detach(), h, alpha)
-    d = lambda t: t.to(DEV).contiguous()
+    hD, hnD, hnnD, actD = h.to(DEV).contiguous(), hn.to(DEV).contiguous(), hnn.to(DEV).contiguous(), act.to(DEV).contiguous()
     partial = torch.empty(16, device=DEV, dtype=torch.float64)
     hdot = torch.empty(M, device=DEV)
-    su8, uu8 = d(safe.to(torch.uint8)), d(unsafe.to(torch.uint8))
-    _C.call('gcbf_loss_partials', _C.ptr(d(h)), _C.ptr(d(hn)), _C.ptr(d(hnn)), _C.ptr(d(act)), a, _C.ptr(su8), _C.ptr(uu8), M,
+    su8, uu8 = safe.to(torch.uint8).to(DEV), unsafe.to(torch.uint8).to(DEV)
+    _C.call('gcbf_loss_partials', _C.ptr(hD), _C.ptr(hnD), _C.ptr(hnnD), _C.ptr(actD), a, _C.ptr(su8), _C.ptr(uu8), M,
             alpha, eps, dt, _C.ptr(partial), _C.ptr(hdot))
     dh, dhn, da, sc = torch.empty(M, device=DEV), torch.empty(M, device=DEV), torch.empty(M, a, device=DEV), torch.empty(8, device=DEV)
-    _C.call('gcbf_loss_grads', _C.ptr(d(h)), _C.ptr(d(hn)), _C.ptr(d(hnn)), _C.ptr(d(act)), a, _C.ptr(su8), _C.ptr(uu8), M,
+    _C.call('gcbf_loss_grads', _C.ptr(hD), _C.ptr(hnD), _C.ptr(hnnD), _C.ptr(actD), a, _C.ptr(su8), _C.ptr(uu8), M,
             alpha, eps, dt, cu, cs, ch, ca, _C.ptr(partial), _C.ptr(dh), _C.ptr(dhn), _C.ptr(da), _C.ptr(sc))
     sc = sc.cpu()
     for got, want in zip(sc[:4].tolist(), [lu.item(), ls.item(), lh.item(), la.item()]):
@@ -272,16 +272,14 @@ def test_loss_kernels_match_reference_formulas():
     assert torch.allclose(dhn.cpu(), hnr.grad.reshape(-1), rtol=1e-5, atol=1e-8)
     assert torch.allclose(da.cpu(), ar.grad, rtol=1e-5, atol=1e-8)
     cnt = torch.empty(1, device=DEV, dtype=torch.int64)
-    _C.call('gcbf_pair_count', _C.ptr(hdot), M, _C.ptr(d(h)), M, alpha, _C.ptr(cnt))
+    _C.call('gcbf_pair_count', _C.ptr(hdot), M, _C.ptr(hD), M, alpha, _C.ptr(cnt))
     assert abs(cnt.item() / (M * M) - acc.item()) < 1e-7
     # empty masks: loss 0, accuracy 1 (gcbf.py:175-177, 187-189)
     z = torch.zeros(M, dtype=torch.uint8, device=DEV)
-    _C.call('gcbf_loss_partials', _C.ptr(d(h)), _C.ptr(d(hn)), _C.ptr(d(hnn)), _C.ptr(d(act)), a, _C.ptr(z), _C.ptr(z), M,
+    _C.call('gcbf_loss_partials', _C.ptr(hD), _C.ptr(hnD), _C.ptr(hnnD), _C.ptr(actD), a, _C.ptr(z), _C.ptr(z), M,
             alpha, eps, dt, _C.ptr(partial), None)
-    _C.call('gcbf_loss_grads', _C.ptr(d(h)), _C.ptr(d(hn)), _C.ptr(d(hnn)), _C.ptr(d(act)), a, _C.ptr(z), _C.ptr(z), M,
-            alpha, eps, dt, cu, cs, ch, ca, _C.ptr(partial), _C.ptr(dh), _C.ptr(dhn), _C.ptr(da), _C.ptr(sc.to(DEV)))
     sc2 = torch.empty(8, device=DEV)
-    _C.call('gcbf_loss_grads', _C.ptr(d(h)), _C.ptr(d(hn)), _C.ptr(d(hnn)), _C.ptr(d(act)), a, _C.ptr(z), _C.ptr(z), M,
+    _C.call('gcbf_loss_grads', _C.ptr(hD), _C.ptr(hnD), _C.ptr(hnnD), _C.ptr(actD), a, _C.ptr(z), _C.ptr(z), M,
             alpha, eps, dt, cu, cs, ch, ca, _C.ptr(partial), _C.ptr(dh), _C.ptr(dhn), _C.ptr(da), _C.ptr(sc2))
     assert sc2[0].item() == 0 and sc2[1].item() == 0 and sc2[4].item() == 1 and sc2[5].item() == 1
 
@@ -378,10 +376,73 @@ def test_cbf_and_actor_forward_backward(env_name, n, obs, B, area):
     ((hg * wh.to(DEV)).sum() + (ug * wu.to(DEV)).sum()).backward()
     assert torch.allclose(hg.detach().cpu(), h.detach(), rtol=0, atol=1e-5), (hg.detach().cpu() - h.detach()).abs().max()
     assert torch.allclose(ug.detach().cpu(), u.detach(), rtol=0, atol=1e-5), (ug.detach().cpu() - u.detach()).abs().max()
-    scale = ea.grad.abs().max().item()
-    assert torch.allclose(data.edge_attr.grad.cpu(), ea.grad, rtol=1e-3, atol=1e-4 * scale)
+    # gradients: relative to each net's gradient norm.  A single ReLU decision flipped by rounding costs ~0.3 % of a
+    # layer's gradient (1/sqrt(#hidden units)); exactness given identical masks is asserted in the next test.
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
+    assert rel(data.edge_attr.grad.cpu(), ea.grad) < 2e-2
     for mod, sdd in ((algo.cbf, cbf_sd), (algo.actor, act_sd)):
+        tot = torch.sqrt(sum((sdd[name].grad.double() ** 2).sum() for name, _ in mod.named_parameters()))
         for name, p in mod.named_parameters():
-            ref = sdd[name].grad
-            tol = 1e-4 * max(ref.abs().max().item(), 1e-8)
-            assert torch.allclose(p.grad.cpu(), ref, rtol=1e-3, atol=tol), (name, (p.grad.cpu() - ref).abs().max().item(), tol)
+            err = (p.grad.cpu().double() - sdd[name].grad.double()).norm() / tot
+            assert err < 1e-2, (name, err.item())
+
+
+def test_net_backward_exact_given_same_relu_masks():
+    """The whole fused backward (head -> gamma -> row scatter -> attention aggregation -> gate -> phi -> edge_attr,
+    incl. the spectral-norm sigma term) against torch autograd in fp64 ON THE SAME ReLU MASKS (taken from the
+    kernels' saved activations), so rounding-level mask flips cannot blur the comparison: tolerance 1e-5 relative."""
+    from gcbf_b200.data import agent_row_index
+    from gcbf_b200.nn.gnn import cached_rowptr
+    sb, env, algo, data, ob = _env_setup('DubinsCar', 24, 6, 3, 1.5, seed=51)
+    layer = algo.cbf.feat_transformer.module_0
+    spec = layer.net_spec(algo.cbf.feat_2_CBF)
+    rowptr = cached_rowptr(data.edge_index, data.x.shape[0])
+    ridx = agent_row_index(data)
+    ea_in = data.edge_attr.detach()
+    out, ctx = ops.net_forward(spec, data.x, ea_in, data.edge_index, rowptr, ridx, None, True)
+    c_phi, c_gate, c_gamma, c_head, msg, att, Nn, E = ctx
+    d_out = torch.randn(out.shape, generator=_g(3)).to(DEV)
+    d_ea, grads = ops.net_backward(spec, ctx, d_out, rowptr, ridx, True)
+
+    dd = lambda t: t.detach().double()
+    leaves = []
+
+    def chain(x, layers, mctx):
+        for i, L in enumerate(layers):
+            W = dd(L.W).requires_grad_(True)
+            b = dd(L.b).requires_grad_(True)
+            leaves.append((W, b))
+            Weff = W
+            if L.sn:
+                u, v = mctx.uv[i]
+                Weff = W / torch.dot(dd(u), W @ dd(v))
+            x = torch.nn.functional.linear(x, Weff, b)
+            if L.act == ops.ACT_RELU:
+                x = x * (mctx.acts[i + 1] > 0).double()       # the kernels' own mask
+            elif L.act == ops.ACT_TANH:
+                x = torch.tanh(x)
+        return x
+    ea64 = dd(ea_in).requires_grad_(True)
+    ei = data.edge_index
+    x64 = dd(data.x)
+    m = chain(torch.cat([x64[ei[1]], x64[ei[0]], ea64], 1), spec.phi, c_phi)
+    gate = chain(m, spec.gate, c_gate)
+    gmax = torch.full((Nn, 1), float('-inf'), dtype=torch.float64, device=DEV).scatter_reduce(
+        0, ei[1].view(-1, 1), gate.detach(), reduce='amax', include_self=True)
+    ex = (gate - gmax[ei[1]]).exp()
+    den = torch.zeros(Nn, 1, dtype=torch.float64, device=DEV).index_add(0, ei[1], ex) + 1e-16
+    aggr = torch.zeros(Nn, 256, dtype=torch.float64, device=DEV).index_add(0, ei[1], ex / den[ei[1]] * m)
+    feat = chain(torch.cat([aggr, x64], 1)[ridx], spec.gamma, c_gamma)
+    h = chain(feat, spec.head, c_head)
+    assert rel_err(out, h) < 1e-5
+    (h * d_out.double()).sum().backward()
+    assert rel_err(d_ea, ea64.grad) < 1e-5, rel_err(d_ea, ea64.grad)
+    names = ['phi'] * 3 + ['gate'] * 3 + ['gamma'] * 3 + ['head'] * 4
+    for i, ((dW, db), (W, b)) in enumerate(zip(grads, leaves)):
+        assert rel_err(dW, W.grad) < 2e-5, (names[i], i, rel_err(dW, W.grad))
+        # (the last gate bias has an exactly-zero gradient -- softmax is shift invariant -- so allow an fp32 noise floor)
+        assert (db.double() - b.grad).norm() <= 2e-5 * b.grad.norm() + 1e-5 * dW.double().norm(), (names[i], i)
+
+
+def rel_err(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-300)).item()
