@@ -24,7 +24,7 @@ import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (os.path.join(ROOT, 'gcbf-pytorch_b200'), os.path.join(ROOT, 'tests')):
+for _p in (os.path.join(ROOT, 'gcbf-pytorch_b200'),):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
@@ -91,7 +91,7 @@ class ClockSampler:
 
 def build_case(cfg_name, device, rank):
     from gcbf_b200 import synth
-    from helpers import seeded_algo
+    from gcbf_b200.synth import seeded_algo
     c = dict(synth.CONFIGS[cfg_name])
     c['seed'] = c['seed'] + 7919 * rank            # every rank owns different graphs (environment-parallel)
     sb = synth.make_states(**c)
@@ -211,6 +211,7 @@ def run_own(args):
 def cpu_sample_step(cfg_name, graphs):
     """Callable running ONE reference train step (oracle port) on the first `graphs` graphs of the config."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import gcbf_oracle as O                      # the ONLY use of oracle/ in bench.py: the CPU baseline
     from gcbf_b200 import synth
     from helpers import oracle_batch, sd_clone, seeded_algo

@@ -47,7 +47,7 @@ def build(force=False, verbose=True):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    cmd = [NVCC, '-shared', '-o', OUT] + objs + ['-lcuda']
+    cmd = [NVCC, '-shared', '-o', OUT] + objs
     subprocess.check_call(cmd)
     return OUT
 

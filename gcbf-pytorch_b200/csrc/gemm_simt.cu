@@ -223,6 +223,17 @@ __global__ void act_bwd_kernel(const float* __restrict__ dY, const float* __rest
   dZ[i] = d;
 }
 
+int launch_colsum(const float* dZ, int ld, int M, int N, float* db, int accumulate, cudaStream_t st) {
+  int rsplit = (int)imin64(64, imax64(1, (int64_t)M / 2048));
+  int rows_per_block = ceil_div(M, rsplit);
+  rsplit = ceil_div(M, rows_per_block);
+  if (rsplit > 1 && !accumulate) GCBF_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * 4, st));
+  dim3 g2(ceil_div(N, 32), rsplit), b2(32, 8);
+  colsum_kernel<<<g2, b2, 0, st>>>(dZ, ld, M, N, db, accumulate, rows_per_block);
+  GCBF_LAUNCH_OK();
+  return GCBF_OK;
+}
+
 int launch_simt_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma,
                     float* Y, int ldy, int M, int N, int K, int act, cudaStream_t st) {
   Epi ep{};
@@ -259,15 +270,7 @@ int launch_simt_wgrad(const float* dZ, int lddz, const float* X, int ldx, const 
   dim3 grid(ceil_div(K, BN), ceil_div(N, BM), splits);
   gemm_simt_kernel<false, false><<<grid, NT, 0, st>>>(dZ, lddz, X, ldx, dW, lddw, N, K, M, k_chunk, ep);
   GCBF_LAUNCH_OK();
-  if (db) {
-    int rsplit = (int)imin64(64, imax64(1, (int64_t)M / 2048));
-    int rows_per_block = ceil_div(M, rsplit);
-    rsplit = ceil_div(M, rows_per_block);
-    if (rsplit > 1 && !accumulate) GCBF_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * 4, st));
-    dim3 g2(ceil_div(N, 32), rsplit), b2(32, 8);
-    colsum_kernel<<<g2, b2, 0, st>>>(dZ, lddz, M, N, db, accumulate, rows_per_block);
-    GCBF_LAUNCH_OK();
-  }
+  if (db) return launch_colsum(dZ, lddz, M, N, db, accumulate, st);
   return GCBF_OK;
 }
 

@@ -11,13 +11,13 @@ int launch_simt_dgrad(const float* dZ, int lddz, const float* W, int ldw, const 
 int launch_simt_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw,
                       float* db, int M, int N, int K, int accumulate, cudaStream_t st);
 #ifdef GCBF_WITH_TCGEN05
-bool tc_fwd_supported(int ldx, int ldw, int ldy, int M, int N, int K);
+bool tc_fwd_supported(int ldx, int ldw, int ldy, int M, int N, int K, bool forced);
 int launch_tc_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
                   int ldy, int M, int N, int K, int act, cudaStream_t st);
-bool tc_dgrad_supported(int lddz, int ldw, int lddx, int M, int N, int K);
+bool tc_dgrad_supported(int lddz, int ldw, int lddx, int M, int N, int K, bool forced);
 int launch_tc_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src,
                     int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
-bool tc_wgrad_supported(int lddz, int ldx, int lddw, int M, int N, int K);
+bool tc_wgrad_supported(int lddz, int ldx, int lddw, int M, int N, int K, bool forced);
 int launch_tc_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw,
                     float* db, int M, int N, int K, int accumulate, cudaStream_t st);
 #endif
@@ -45,7 +45,7 @@ extern "C" int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw,
   GCBF_REQUIRE(X && W && Y, "gcbf_linear_fwd: null pointer");
   cudaStream_t st = as_stream(stream);
 #ifdef GCBF_WITH_TCGEN05
-  if (impl != 1 && tc_fwd_supported(ldx, ldw, ldy, M, N, K)) { g_last_impl = 2;
+  if (impl != 1 && tc_fwd_supported(ldx, ldw, ldy, M, N, K, impl == 2)) { g_last_impl = 2;
     return launch_tc_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st); }
 #endif
   if (impl == 2) { set_error("gcbf_linear_fwd: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
@@ -62,7 +62,7 @@ extern "C" int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, i
   GCBF_REQUIRE(dZ && W && dX, "gcbf_linear_bwd_data: null pointer");
   cudaStream_t st = as_stream(stream);
 #ifdef GCBF_WITH_TCGEN05
-  if (impl != 1 && tc_dgrad_supported(lddz, ldw, lddx, M, N, K)) { g_last_impl = 2;
+  if (impl != 1 && tc_dgrad_supported(lddz, ldw, lddx, M, N, K, impl == 2)) { g_last_impl = 2;
     return launch_tc_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st); }
 #endif
   if (impl == 2) { set_error("gcbf_linear_bwd_data: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
@@ -85,7 +85,7 @@ extern "C" int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X,
   }
   GCBF_REQUIRE(dZ && X, "gcbf_linear_bwd_weight: null pointer");
 #ifdef GCBF_WITH_TCGEN05
-  if (impl != 1 && tc_wgrad_supported(lddz, ldx, lddw, M, N, K)) { g_last_impl = 2;
+  if (impl != 1 && tc_wgrad_supported(lddz, ldx, lddw, M, N, K, impl == 2)) { g_last_impl = 2;
     return launch_tc_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st); }
 #endif
   if (impl == 2) { set_error("gcbf_linear_bwd_weight: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }

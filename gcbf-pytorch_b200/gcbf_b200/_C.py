@@ -35,6 +35,8 @@ _SIGS = {
     'gcbf_linear_fwd': (c_int, [P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_linear_bwd_data': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_linear_bwd_weight': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'gcbf_set_gemm_workspace': (c_int, [P, c_size_t]),
+    'gcbf_gemm_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'gcbf_act_bwd': (c_int, [P, P, P, c_int64, c_int, P]),
     'gcbf_attn_aggr_fwd': (c_int, [P, c_int, P, P, c_int, c_int, P, P, c_int, P]),
     'gcbf_attn_aggr_bwd': (c_int, [P, c_int, P, P, c_int, c_int, P, c_int, P, c_int, P, c_int, P]),

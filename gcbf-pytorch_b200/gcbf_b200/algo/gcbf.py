@@ -121,11 +121,12 @@ class GCBF(Algorithm):
             self._bucket = _FlatBucket([self.cbf, self.actor], self.device)
         return self._bucket
 
-    def _world(self):
-        import torch.distributed as dist
-        if self.process_group is None and not (dist.is_available() and dist.is_initialized()):
-            return None, 1
-        return dist, dist.get_world_size(self.process_group)
+    def _reducer(self):
+        from ..distributed import Reducer
+        red = getattr(self, '_red', None)
+        if red is None or red.group is not self.process_group:
+            red = self._red = Reducer(self.process_group)
+        return red
 
     def train_step(self, graphs, apply_optim: bool = True, compute_acc_h_dot: bool = True) -> Dict[str, Tensor]:
         """One inner iteration of GCBF.update (gcbf.py:158-226) on a collated batch.  Returns device tensors
@@ -134,7 +135,8 @@ class GCBF(Algorithm):
         env, hp = self._env, self.params
         bucket = self._ensure_bucket()
         dev = graphs.states.device
-        dist, world = self._world()
+        red = self._reducer()
+        world = red.world
         M = graphs.u_ref.shape[0]
         a_dim = self.action_dim
 
@@ -155,8 +157,7 @@ class GCBF(Algorithm):
         dt = float(env.dt)
         _C.call('gcbf_loss_partials', _C.ptr(hd), _C.ptr(hnd), _C.ptr(hnnd), _C.ptr(actd), a_dim, _C.ptr(safe_u8),
                 _C.ptr(unsafe_u8), M, float(hp['alpha']), float(hp['eps']), dt, _C.ptr(partial), _C.ptr(hdot))
-        if world > 1:
-            dist.all_reduce(partial, group=self.process_group)           # global counts => global masked means
+        red.sum_(partial)                                                # global counts => global masked means
         d_h = torch.empty_like(hd)
         d_hn = torch.empty_like(hnd)
         d_act = torch.empty_like(actd)
@@ -173,18 +174,12 @@ class GCBF(Algorithm):
                    unsafe_mask=masks[1], edge_index_new=relinked.edge_index, hdot=hdot)
         if compute_acc_h_dot:                                            # gcbf.py:209 (M x M broadcast mean)
             cnt = torch.empty(1, device=dev, dtype=torch.int64)
-            if world > 1:
-                hdot_all = torch.empty(world * M, device=dev, dtype=torch.float32)
-                dist.all_gather_into_tensor(hdot_all, hdot, group=self.process_group)
-            else:
-                hdot_all = hdot
+            hdot_all = red.gather_cat(hdot)
             _C.call('gcbf_pair_count', _C.ptr(hdot_all), hdot_all.numel(), _C.ptr(hd), M, float(hp['alpha']), _C.ptr(cnt))
-            if world > 1:
-                dist.all_reduce(cnt, group=self.process_group)
+            red.sum_(cnt)
             out['acc_h_dot'] = cnt.to(torch.float64) / float(world * M) / float(world * M)
 
-        if world > 1:
-            dist.all_reduce(bucket.grad, group=self.process_group)       # the ONE gradient collective (K9)
+        red.sum_(bucket.grad)                                            # the ONE gradient collective (K9)
         if apply_optim:
             self.optim_step()
         return out

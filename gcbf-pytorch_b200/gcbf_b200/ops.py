@@ -78,6 +78,31 @@ def _mat(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
 # ----------------------------------------------------------------------------------------------------
 # raw ops (each = one C-ABI entry point)
 # ----------------------------------------------------------------------------------------------------
+_GEMM_WS = {'buf': None, 'bytes': 0}
+USE_TCGEN05 = True     # set False to keep every layer on the fp32 SIMT kernel
+
+
+def _ensure_gemm_ws(M, N, K, device):
+    """The C library never allocates: register a scratch buffer big enough for this layer's tcgen05 operands."""
+    if not USE_TCGEN05 or GEMM_IMPL == 1 or (M < 256 and GEMM_IMPL != 2):
+        return
+    lib = _C.lib()
+    if not lib.gcbf_has_tcgen05():
+        return
+    need = int(lib.gcbf_gemm_workspace_bytes(M, N, K))
+    if need > _GEMM_WS['bytes']:
+        size = int(need * 1.1) + (1 << 20)
+        _GEMM_WS['buf'] = torch.empty(size, device=device, dtype=torch.uint8)
+        _GEMM_WS['bytes'] = size
+        lib.gcbf_set_gemm_workspace(_GEMM_WS['buf'].data_ptr(), size)
+
+
+def release_gemm_workspace():
+    if _GEMM_WS['buf'] is not None:
+        _C.lib().gcbf_set_gemm_workspace(None, 0)
+    _GEMM_WS['buf'], _GEMM_WS['bytes'] = None, 0
+
+
 def linear_fwd(x, W, b, inv_sigma, act, out=None):
     x, ldx = _mat(x)
     W, ldw = _mat(W)
@@ -88,6 +113,7 @@ def linear_fwd(x, W, b, inv_sigma, act, out=None):
         out = torch.empty(M, N, device=x.device, dtype=torch.float32)
     y, ldy = _mat(out)
     assert y.data_ptr() == out.data_ptr()
+    _ensure_gemm_ws(M, N, K, x.device)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_fwd', ptr(x), ldx, ptr(W), ldw, ptr(b), ptr(inv_sigma), ptr(y), ldy,
                                                  M, N, K, act, GEMM_IMPL))
     return out
@@ -107,6 +133,7 @@ def linear_bwd_data(dz, W, inv_sigma, relu_src, out=None, accumulate=False):
     rs, ldr = (None, 0)
     if relu_src is not None:
         rs, ldr = _mat(relu_src)
+    _ensure_gemm_ws(M, N, K, dz.device)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_data', ptr(dz), lddz, ptr(W), ldw, ptr(inv_sigma), ptr(rs), ldr,
                                                  ptr(o), ldo, M, N, K, 1 if accumulate else 0, GEMM_IMPL))
     return out
@@ -119,6 +146,7 @@ def linear_bwd_weight(dz, x, inv_sigma, need_bias=True):
     K = x.shape[1]
     dW = torch.empty(N, K, device=dz.device, dtype=torch.float32)
     db = torch.empty(N, device=dz.device, dtype=torch.float32) if need_bias else None
+    _ensure_gemm_ws(M, N, K, dz.device)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_weight', ptr(dz), lddz, ptr(x), ldx, ptr(inv_sigma), ptr(dW), K,
                                                  ptr(db), M, N, K, 0, GEMM_IMPL))
     return dW, db

@@ -87,3 +87,30 @@ CONFIGS = {
     'C4': dict(env='SimpleDrone', num_agents=1024, num_obs=1024, num_graphs=16, area_size=8.0, seed=1004),
     'C5': dict(env='DubinsCar', num_agents=4096, num_obs=128, num_graphs=8, area_size=16.0, seed=1005),
 }
+
+
+def seeded_algo(env_name, n, device, init_seed=0, env_params=None, hyperparams='table'):
+    """gcbf_b200 env + GCBF with the reference's seeded initialisation: torch.manual_seed(init_seed) followed by the
+    same construction order as reference gcbf/algo/gcbf.py:87-100 gives the same weights (up to LAPACK's QR in
+    orthogonal_, which is not bit-reproducible across host CPUs)."""
+    import torch
+    from .algo import make_algo
+    from .env import make_env
+    from .trainer.utils import read_params
+    env = make_env(env_name, n, device)
+    params = env.default_params
+    if env_params:
+        params.update(env_params)
+    env = make_env(env_name, n, device, params=params)
+    torch.manual_seed(init_seed)
+    hp = read_params(env_name, 'gcbf') if hyperparams == 'table' else hyperparams
+    algo = make_algo('gcbf', env, n, env.node_dim, env.edge_dim, env.action_dim, device, 512, hp)
+    return env, algo
+
+
+def product_batch(env, sb, device):
+    """gcbf_b200 graph for a SynthBatch: goal installed, radius graph + edge features + u_ref from the kernels."""
+    env.set_goal(sb.goals)
+    if sb.env == 'DubinsCar':
+        env._obs = sb.obs.to(device)
+    return env.graph_from_states(sb.states.to(device))

@@ -102,6 +102,11 @@ int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, int ldw, con
 int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma,
                            float* dW, int lddw, float* db, int M, int N, int K, int accumulate, int impl,
                            void* stream);
+/* Scratch for the tcgen05 path ([hi; lo] operand copies).  The library never allocates: the caller registers a
+ * device buffer (process-wide; NULL unregisters, which routes every layer to the fp32 SIMT kernel) of at least
+ * gcbf_gemm_workspace_bytes(M, N, K) bytes for the largest layer it will run. */
+int gcbf_set_gemm_workspace(void* device_ptr, size_t bytes);
+size_t gcbf_gemm_workspace_bytes(int M, int N, int K);
 /* dZ = dY * act'(Y) for the output activation (tanh: 1 - Y^2; relu: Y > 0).  In place allowed. */
 int gcbf_act_bwd(const float* dY, const float* Y, float* dZ, int64_t count, int act, void* stream);
 

@@ -13,20 +13,7 @@ def case_inputs(meta):
     return sb
 
 
-def seeded_algo(env_name, n, device, init_seed=0, env_params=None, hyperparams='table'):
-    """gcbf_b200 env + GCBF with the reference's seeded initialisation."""
-    from gcbf_b200.algo import make_algo
-    from gcbf_b200.env import make_env
-    from gcbf_b200.trainer.utils import read_params
-    env = make_env(env_name, n, device)
-    params = env.default_params
-    if env_params:
-        params.update(env_params)
-    env = make_env(env_name, n, device, params=params)
-    torch.manual_seed(init_seed)
-    hp = read_params(env_name, 'gcbf') if hyperparams == 'table' else hyperparams
-    algo = make_algo('gcbf', env, n, env.node_dim, env.edge_dim, env.action_dim, device, 512, hp)
-    return env, algo
+from gcbf_b200.synth import seeded_algo, product_batch  # noqa: E402,F401
 
 
 def oracle_batch(sb):
@@ -39,14 +26,6 @@ def oracle_batch(sb):
     ag = sb.states if am is None else sb.states[am]
     ur = O.u_ref(env, ag, sb.goals, K)
     return dict(edge_index=ei, K=K, x=x, agent_mask=am, u_ref=ur, N=N)
-
-
-def product_batch(env, sb, device):
-    """gcbf_b200 graph for a SynthBatch: goal installed, radius graph + u_ref from the kernels."""
-    env.set_goal(sb.goals)
-    if sb.env == 'DubinsCar':
-        env._obs = sb.obs.to(device)
-    return env.graph_from_states(sb.states.to(device))
 
 
 def sd_clone(module):

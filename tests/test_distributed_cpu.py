@@ -1,0 +1,83 @@
+"""world_size-2 gloo tests (CPU) of the host-side data-parallel logic: graph sharding, the reduction of the loss
+partial sums to global masked means, the h_dot gather and the single flat-bucket gradient all-reduce."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gcbf_b200.distributed import Reducer, shard_range
+
+
+def test_shard_range_partitions_everything():
+    for n in (1, 7, 32, 33):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _partials(h, safe, unsafe, eps=0.02):
+    """torch restatement of the first six entries of gcbf_loss_partials (sum / count / ok for unsafe and safe)."""
+    p = torch.zeros(16, dtype=torch.float64)
+    p[0] = torch.relu(h[unsafe] + eps).double().sum()
+    p[1] = unsafe.sum()
+    p[2] = (h[unsafe] < 0).sum()
+    p[3] = torch.relu(-h[safe] + eps).double().sum()
+    p[4] = safe.sum()
+    p[5] = (h[safe] >= 0).sum()
+    p[7] = h.numel()
+    return p
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        red = Reducer()
+        assert red.world == world and red.rank == rank
+        g = torch.Generator().manual_seed(0)
+        B, n = 6, 5
+        h = torch.randn(B * n, generator=g) * 0.05
+        safe = torch.rand(B * n, generator=g) < 0.5
+        unsafe = (torch.rand(B * n, generator=g) < 0.3) & ~safe
+        lo, hi = shard_range(B, world, rank)
+        sl = slice(lo * n, hi * n)
+        # 1. partial sums: reduced local partials == partials of the whole batch -> identical masked means on all ranks
+        p = red.sum_(_partials(h[sl], safe[sl], unsafe[sl]))
+        assert torch.allclose(p, _partials(h, safe, unsafe), rtol=1e-12, atol=1e-12)
+        # 2. h_dot gather keeps rank order
+        hd = red.gather_cat(h[sl].clone())
+        assert torch.equal(hd, h)
+        # 3. one flat-bucket all-reduce == sum of the per-rank gradients; weights stay replicated
+        from gcbf_b200.algo.gcbf import _FlatBucket
+        torch.manual_seed(3)
+        net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+        bucket = _FlatBucket([net[0], net[1]], torch.device('cpu'))
+        x = torch.randn(8, 4, generator=g)
+        xs = x[rank::world]
+        bucket.zero_grad()
+        net(xs).square().sum().backward()
+        assert net[0].weight.grad.data_ptr() == bucket.grad.data_ptr()          # autograd accumulated in place
+        red.sum_(bucket.grad)
+        ref = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+        ref.load_state_dict(net.state_dict())
+        ref(x).square().sum().backward()
+        flat_ref = torch.cat([p_.grad.reshape(-1) for p_ in ref.parameters()])
+        assert torch.allclose(bucket.grad, flat_ref, rtol=1e-5, atol=1e-6)
+        assert bucket.ranges == [(0, 15), (15, 23)]
+        torch.save(bucket.grad.clone(), os.path.join(tmp, f'g{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_reductions(tmp_path):
+    import socket
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g0, g1 = torch.load(tmp_path / 'g0.pt'), torch.load(tmp_path / 'g1.pt')
+    assert torch.equal(g0, g1)       # every rank ends up with the same reduced gradient
