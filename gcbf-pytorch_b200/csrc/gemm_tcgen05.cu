@@ -26,7 +26,8 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // fp32 elements per k-block = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 8;              // tf32: 32 bytes per instruction
-constexpr int NUM_THREADS = 192;       // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 epilogue / fp32 chunk accumulation
+constexpr int KCH = 8;                 // k-blocks (of 32) accumulated inside the tensor core before promotion to registers
 constexpr int MAX_CHUNK_ROWS = 65536;  // rows of the big operand processed per launch (bounds the scratch)
 
 enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
@@ -179,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * 32); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * 32); }
     fence_barrier_init();
   }
   if (warp == 1) {            // one warp allocates TMEM and later frees it
@@ -213,6 +214,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     } else if (warp == 1) {
       // ===== MMA issuer (single thread) =====
+      // The tensor core's fp32 accumulator truncates on every MMA (tools/acc_probe.py: bias ~ -K/8 * 2^-24), so K is
+      // consumed in chunks of KCH*32 = 256 elements: each chunk starts a fresh TMEM accumulator (double-buffered) and the
+      // epilogue warps add the chunk sums in registers with round-to-nearest.
       if (lane == 0) {
         constexpr uint32_t idesc = make_idesc(BM, BN);
         int stage = 0;
@@ -220,54 +224,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int buf = 0;
         uint32_t tphase[2] = {0, 0};
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-          mbar_wait(&tempty[buf], tphase[buf] ^ 1);          // epilogue has drained this accumulator
-          tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&full[stage], phase);
+          for (int kc = 0; kc < nkb; kc += KCH) {
+            mbar_wait(&tempty[buf], tphase[buf] ^ 1);        // epilogue has drained this accumulator
             tcgen05_fence_after();
-            const uint32_t st = smem_u32(smem + stage * K::STAGE_BYTES);
-            const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + K::A_BYTES);
-            const uint64_t b_hi = make_smem_desc(st + 2 * K::A_BYTES), b_lo = make_smem_desc(st + 2 * K::A_BYTES + K::B_BYTES);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+            const int kend = min(nkb, kc + KCH);
+            for (int kb = kc; kb < kend; ++kb) {
+              mbar_wait(&full[stage], phase);
+              tcgen05_fence_after();
+              const uint32_t st = smem_u32(smem + stage * K::STAGE_BYTES);
+              const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + K::A_BYTES);
+              const uint64_t b_hi = make_smem_desc(st + 2 * K::A_BYTES), b_lo = make_smem_desc(st + 2 * K::A_BYTES + K::B_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-              const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);   // +32 B per k-slice inside the 128 B swizzle row
-              umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-              umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);   // +32 B per k-slice inside the 128 B swizzle row
+                umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb > kc || kk > 0) ? 1u : 0u);
+                umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+              }
+              umma_commit(&empty[stage]);                     // smem slot free once these MMAs retire
+              if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&empty[stage]);                       // smem slot free once these MMAs retire
-            if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+            umma_commit(&tfull[buf]);                          // chunk sum complete -> epilogue
+            tphase[buf] ^= 1;
+            buf ^= 1;
           }
-          umma_commit(&tfull[buf]);                            // accumulator complete -> epilogue
-          tphase[buf] ^= 1;
-          buf ^= 1;
         }
       }
     } else {
-      // ===== epilogue warps 2..5: TMEM lane group = warp % 4 =====
+      // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+      constexpr int CH = BN / 2;                               // columns owned by one thread
       const int lg = warp & 3;
+      const int chalf = (warp - 2) >> 2;
       const float alpha = ep.alpha ? __ldg(ep.alpha) : 1.f;
       int buf = 0;
       uint32_t tphase[2] = {0, 0};
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
-        mbar_wait(&tfull[buf], tphase[buf]);
-        tcgen05_fence_after();
+        float acc[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+        for (int kc = 0; kc < nkb; kc += KCH) {
+          mbar_wait(&tfull[buf], tphase[buf]);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + chalf * CH) + ((uint32_t)(lg * 32) << 16);
+#pragma unroll
+          for (int c = 0; c < CH / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __fadd_rn(acc[c * 32 + j], __uint_as_float(r[j]));
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&tempty[buf]);
+          tphase[buf] ^= 1;
+          buf ^= 1;
+        }
         const int row = m0 + lg * 32 + lane;
-        const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(lg * 32) << 16);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
-          tmem_ld_wait();
-          const int col0 = n0 + c * 32;
-          if (row < Mo && col0 < No) {
+        if (row < Mo) {
+#pragma unroll
+          for (int c = 0; c < CH / 32; ++c) {
+            const int col0 = n0 + chalf * CH + c * 32;
+            if (col0 >= No) continue;
             float* dst = C + (size_t)row * ldc + col0;
             const int nv = min(32, No - col0);
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = alpha * __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) v[j] = alpha * acc[c * 32 + j];
             if (ep.mode == EPI_FWD) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -302,10 +326,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         }
-        tcgen05_fence_before();
-        mbar_arrive(&tempty[buf]);
-        tphase[buf] ^= 1;
-        buf ^= 1;
       }
     }
   }
@@ -326,25 +346,47 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }
 
 // dst_hi[r][c] (r < R_pad, c < C_pad), element (r, c) = TRANS ? src[c][r] : src[r][c]; zero outside [rows, cols)
+constexpr int TRANS_STRIP = 16;   // column tiles (of 32) per block in the transposing split
+
 template <bool TRANS>
 __global__ void split_kernel(const float* __restrict__ src, int ld, int rows, int cols, float* __restrict__ dst_hi,
-                             float* __restrict__ dst_lo, int R_pad, int C_pad) {
+                             float* __restrict__ dst_lo, int R_pad, int C_pad, float* __restrict__ rowsum, int strip) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   if (TRANS) {
-    // source is [cols(src rows)][rows(src cols)]: read coalesced along r (source columns)
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int c = c0 + i, r = r0 + threadIdx.x;
-      tile[i][threadIdx.x] = (c < cols && r < rows) ? src[(size_t)c * ld + r] : 0.f;
+    // source is [cols(src rows)][rows(src cols)]: read coalesced along r (source columns).  One block walks a strip of
+    // TRANS_STRIP column tiles so the fused row sums need one atomic per row per strip (same-address atomics from many
+    // blocks serialise in L2).
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ct = 0; ct < strip; ++ct) {
+      const int cb = c0 * strip + ct * 32;
+      if (cb >= C_pad) break;
+      __syncthreads();
+      for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = cb + i, r = r0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < cols && r < rows) ? src[(size_t)c * ld + r] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = threadIdx.y + 8 * k;
+        const int r = r0 + i, c = cb + threadIdx.x;
+        const float x = tile[threadIdx.x][i];
+        if (r < R_pad && c < C_pad) {
+          float hi, lo;
+          split_tf32(x, hi, lo);
+          dst_hi[(size_t)r * C_pad + c] = hi;
+          dst_lo[(size_t)r * C_pad + c] = lo;
+        }
+        rs[k] += x;
+      }
     }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      const int r = r0 + i, c = c0 + threadIdx.x;
-      if (r < R_pad && c < C_pad) {
-        float hi, lo;
-        split_tf32(tile[threadIdx.x][i], hi, lo);
-        dst_hi[(size_t)r * C_pad + c] = hi;
-        dst_lo[(size_t)r * C_pad + c] = lo;
+    if (rowsum) {   // fused bias gradient: sum over the (transposed) columns = column sums of the source
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float s = warp_sum(rs[k]);
+        const int r = r0 + threadIdx.y + 8 * k;
+        if (threadIdx.x == 0 && r < rows) atomicAdd(rowsum + r, s);
       }
     }
   } else {
@@ -404,13 +446,15 @@ static size_t operand_bytes(int rows, int cols, int tile_rows) {
   return (size_t)2 * round_up(rows, tile_rows) * round_up(cols, BK) * 4;
 }
 
-static int prep_operand(const Operand& op, int tile_rows, float* dst, int* R_pad_out, int* C_pad_out, cudaStream_t st) {
+static int prep_operand(const Operand& op, int tile_rows, float* dst, int* R_pad_out, int* C_pad_out, cudaStream_t st,
+                        float* rowsum = nullptr) {
   const int R_pad = round_up(op.rows, tile_rows), C_pad = round_up(op.cols, BK);
   float* hi = dst;
   float* lo = dst + (size_t)R_pad * C_pad;
-  dim3 grid(C_pad / 32, ceil_div(R_pad, 32)), block(32, 8);
-  if (op.trans) split_kernel<true><<<grid, block, 0, st>>>(op.src, op.ld, op.rows, op.cols, hi, lo, R_pad, C_pad);
-  else split_kernel<false><<<grid, block, 0, st>>>(op.src, op.ld, op.rows, op.cols, hi, lo, R_pad, C_pad);
+  const int strip = (op.trans && rowsum) ? TRANS_STRIP : 1;   // long strips only where they save same-address atomics
+  dim3 grid(ceil_div(C_pad, 32 * strip), ceil_div(R_pad, 32)), block(32, 8);
+  if (op.trans) split_kernel<true><<<grid, block, 0, st>>>(op.src, op.ld, op.rows, op.cols, hi, lo, R_pad, C_pad, rowsum, strip);
+  else split_kernel<false><<<grid, block, 0, st>>>(op.src, op.ld, op.rows, op.cols, hi, lo, R_pad, C_pad, nullptr, 1);
   GCBF_LAUNCH_OK();
   *R_pad_out = R_pad; *C_pad_out = C_pad;
   return GCBF_OK;
@@ -443,7 +487,7 @@ static int launch_tiles(const float* a_scr, int RA, const float* b_scr, int RB, 
 }
 
 // D[Mo,No] = A * B^T with A logical [Mo][Kc], B logical [No][Kc]; chunked over Mo (fwd/dgrad) or Kc (wgrad)
-static int run_gemm(Operand A, Operand B, float* C, int ldc, EpiParams ep, bool chunk_k, cudaStream_t st) {
+static int run_gemm(Operand A, Operand B, float* C, int ldc, EpiParams ep, bool chunk_k, cudaStream_t st, float* a_rowsum = nullptr) {
   const int Mo = A.rows, No = B.rows, Kc = A.cols;
   const int BN = (No > 128) ? 256 : 128;
   if (!g_ws) { set_error("tcgen05 GEMM: no workspace registered (gcbf_set_gemm_workspace)"); return GCBF_E_INVALID; }
@@ -480,7 +524,7 @@ static int run_gemm(Operand A, Operand B, float* C, int ldc, EpiParams ep, bool 
     if (need > g_ws_bytes) { set_error("tcgen05 GEMM: workspace too small (%zu > %zu)", need, g_ws_bytes); return GCBF_E_INVALID; }
     int RA, RB, Kp, Kp2;
     float* a_scr = g_ws;
-    if (int rc = prep_operand(a, BM, a_scr, &RA, &Kp, st)) return rc;
+    if (int rc = prep_operand(a, BM, a_scr, &RA, &Kp, st, a_rowsum)) return rc;
     float* b_scr = g_ws + (size_t)2 * RA * Kp;
     if (int rc = prep_operand(b, BN, b_scr, &RB, &Kp2, st)) return rc;
     const int tiles = (RA / BM) * (RB / BN);
@@ -529,8 +573,9 @@ int launch_tc_wgrad(const float* dZ, int lddz, const float* X, int ldx, const fl
   tc::EpiParams ep{};
   ep.mode = tc::EPI_WGRAD; ep.alpha = inv_sigma; ep.accumulate = accumulate;
   // dW[N,K] = dZ^T[N,M] * X[M,K]: A = dZ^T ([N][M]), B = X^T ([K][M]); contraction over the M batch rows
-  if (int rc = tc::run_gemm({dZ, lddz, N, M, true}, {X, ldx, K, M, true}, dW, lddw, ep, true, st)) return rc;
-  if (db) return launch_colsum(dZ, lddz, M, N, db, accumulate, st);
+  // the bias gradient (column sums of dZ) is fused into the transposing split of dZ
+  if (db && !accumulate) GCBF_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * 4, st));
+  if (int rc = tc::run_gemm({dZ, lddz, N, M, true}, {X, ldx, K, M, true}, dW, lddw, ep, true, st, db)) return rc;
   return GCBF_OK;
 }
 

@@ -132,6 +132,14 @@ class GCBF(Algorithm):
         """One inner iteration of GCBF.update (gcbf.py:158-226) on a collated batch.  Returns device tensors
         (no host sync): 'scalars' = [loss_unsafe, loss_safe, loss_h_dot, loss_action, acc_unsafe, acc_safe,
         total_loss, num_agents], 'acc_h_dot', plus h / actions / h_next / h_next_new for inspection."""
+        from ..arena import ARENA
+        ARENA.begin(graphs.states.device)      # every activation / gradient below is a view into the step arena
+        try:
+            return self._train_step(graphs, apply_optim, compute_acc_h_dot)
+        finally:
+            ARENA.end()
+
+    def _train_step(self, graphs, apply_optim: bool, compute_acc_h_dot: bool) -> Dict[str, Tensor]:
         env, hp = self._env, self.params
         bucket = self._ensure_bucket()
         dev = graphs.states.device
@@ -170,8 +178,9 @@ class GCBF(Algorithm):
         bucket.zero_grad()                                               # gcbf.py:220-221
         torch.autograd.backward([h, h_next, actions], [d_h, d_hn, d_act])  # gcbf.py:222
 
-        out = dict(scalars=scalars, h=hd, actions=actd, h_next=hnd, h_next_new=hnnd, safe_mask=masks[0],
-                   unsafe_mask=masks[1], edge_index_new=relinked.edge_index, hdot=hdot)
+        # results leave the arena as private copies (tiny: O(num_agents))
+        out = dict(scalars=scalars, h=hd.clone(), actions=actd.clone(), h_next=hnd.clone(), h_next_new=hnnd.clone(),
+                   safe_mask=masks[0], unsafe_mask=masks[1], edge_index_new=relinked.edge_index, hdot=hdot)
         if compute_acc_h_dot:                                            # gcbf.py:209 (M x M broadcast mean)
             cnt = torch.empty(1, device=dev, dtype=torch.int64)
             hdot_all = red.gather_cat(hdot)

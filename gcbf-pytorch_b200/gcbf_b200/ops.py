@@ -16,6 +16,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _C
+from .arena import ARENA, empty as _empty, zeros as _zeros
 from ._C import call, ptr
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
@@ -110,7 +111,7 @@ def linear_fwd(x, W, b, inv_sigma, act, out=None):
     N = W.shape[0]
     assert W.shape[1] == K, (x.shape, W.shape)
     if out is None:
-        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        out = _empty(M, N, device=x.device, dtype=torch.float32)
     y, ldy = _mat(out)
     assert y.data_ptr() == out.data_ptr()
     _ensure_gemm_ws(M, N, K, x.device)
@@ -127,7 +128,7 @@ def linear_bwd_data(dz, W, inv_sigma, relu_src, out=None, accumulate=False):
     assert W.shape[0] == N
     if out is None:
         assert not accumulate
-        out = torch.empty(M, K, device=dz.device, dtype=torch.float32)
+        out = _empty(M, K, device=dz.device, dtype=torch.float32)
     o, ldo = _mat(out)
     assert o.data_ptr() == out.data_ptr()
     rs, ldr = (None, 0)
@@ -144,8 +145,8 @@ def linear_bwd_weight(dz, x, inv_sigma, need_bias=True):
     x, ldx = _mat(x)
     M, N = dz.shape
     K = x.shape[1]
-    dW = torch.empty(N, K, device=dz.device, dtype=torch.float32)
-    db = torch.empty(N, device=dz.device, dtype=torch.float32) if need_bias else None
+    dW = _empty(N, K, device=dz.device, dtype=torch.float32)
+    db = _empty(N, device=dz.device, dtype=torch.float32) if need_bias else None
     _ensure_gemm_ws(M, N, K, dz.device)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_weight', ptr(dz), lddz, ptr(x), ldx, ptr(inv_sigma), ptr(dW), K,
                                                  ptr(db), M, N, K, 0, GEMM_IMPL))
@@ -155,7 +156,7 @@ def linear_bwd_weight(dz, x, inv_sigma, need_bias=True):
 def act_bwd(dy, y, act):
     dy = dy.contiguous()
     y = y.contiguous()
-    out = torch.empty_like(dy)
+    out = _empty(dy.shape, device=dy.device, dtype=dy.dtype)
     call('gcbf_act_bwd', ptr(dy), ptr(y), ptr(out), dy.numel(), act)
     return out
 
@@ -248,7 +249,7 @@ def edge_attr_fwd(env_id: int, states, edge_index):
     ei = edge_index.contiguous()
     E = ei.shape[1]
     ed = {0: 4, 1: 5, 2: 6}[env_id]
-    out = torch.empty(E, ed, device=st.device, dtype=torch.float32)
+    out = _empty(E, ed, device=st.device, dtype=torch.float32)
     call('gcbf_edge_attr_fwd', env_id, ptr(st), ld, ptr(ei) if E else None, E, ptr(out) if E else None)
     return out
 
@@ -257,7 +258,7 @@ def edge_attr_bwd(env_id: int, states, edge_index, d_edge_attr):
     st, ld = _mat(states)
     ei = edge_index.contiguous()
     E = ei.shape[1]
-    d_states = torch.zeros(st.shape[0], ld, device=st.device, dtype=torch.float32)
+    d_states = _zeros(st.shape[0], ld, device=st.device, dtype=torch.float32)
     d_ea = d_edge_attr.contiguous()
     call('gcbf_edge_attr_bwd', env_id, ptr(st), ld, ptr(ei) if E else None, E, ptr(d_ea) if E else None, ptr(d_states))
     return d_states[:, :st.shape[1]]
@@ -406,19 +407,19 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
     ei = edge_index.contiguous()
     xc = x.contiguous()
     ea = edge_attr.contiguous()
-    ein = torch.empty(E, kin, device=dev, dtype=torch.float32)
+    ein = _empty(E, kin, device=dev, dtype=torch.float32)
     call('gcbf_edge_input_fwd', ptr(xc), spec.node_dim, ptr(ea) if E else None, spec.edge_dim, ptr(ei) if E else None,
          E, ptr(ein) if E else None, kin)
     msg, c_phi = mlp_forward(ein, spec.phi, save)                        # gnn.py:30-32
     gate, c_gate = mlp_forward(msg, spec.gate, save)                     # AttentionalAggregation.gate_nn
     C = spec.phi_dim
-    gin_all = torch.empty(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
-    att = torch.empty(E, device=dev, dtype=torch.float32)
+    gin_all = _empty(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
+    att = _empty(E, device=dev, dtype=torch.float32)
     call('gcbf_attn_aggr_fwd', ptr(msg) if E else None, C, ptr(gate) if E else None, ptr(rowptr), Nn, C,
          ptr(att) if E else None, ptr(gin_all), C + spec.node_dim)
     copy2d(xc, gin_all[:, C:], Nn, spec.node_dim)                        # cat([aggr_out, x])  gnn.py:35
     if row_index is not None:
-        gin = torch.empty(row_index.numel(), C + spec.node_dim, device=dev, dtype=torch.float32)
+        gin = _empty(row_index.numel(), C + spec.node_dim, device=dev, dtype=torch.float32)
         rows_gather(gin_all, row_index, gin)
     else:
         gin = gin_all
@@ -429,7 +430,7 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
     if spec.head is not None:
         if head_extra is not None:                                       # cat([x, data.u_ref])  gnn_controller.py:46
             R, F = feat.shape
-            hin = torch.empty(R, F + head_extra.shape[1], device=dev, dtype=torch.float32)
+            hin = _empty(R, F + head_extra.shape[1], device=dev, dtype=torch.float32)
             copy2d(feat, hin, R, F)
             copy2d(head_extra.contiguous(), hin[:, F:], R, head_extra.shape[1])
         else:
@@ -451,12 +452,12 @@ def net_backward(spec: NetSpec, ctx, d_out, rowptr, row_index, need_d_edge_attr)
         d_feat = d_hin[:, :F] if d_hin.shape[1] != F else d_hin           # strided view: kernels take ld
     d_gin, g_gamma = mlp_backward(c_gamma, spec.gamma, d_feat, True)
     if row_index is not None:
-        d_gin_all = torch.zeros(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
+        d_gin_all = _zeros(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
         rows_scatter(d_gin, row_index, d_gin_all)
     else:
         d_gin_all = d_gin
-    d_msg = torch.empty(E, C, device=dev, dtype=torch.float32)
-    d_gate = torch.empty(E, 1, device=dev, dtype=torch.float32)
+    d_msg = _empty(E, C, device=dev, dtype=torch.float32)
+    d_gate = _empty(E, 1, device=dev, dtype=torch.float32)
     call('gcbf_attn_aggr_bwd', ptr(msg) if E else None, C, ptr(att) if E else None, ptr(rowptr), Nn, C, ptr(d_gin_all),
          C + spec.node_dim, ptr(d_msg) if E else None, C, ptr(d_gate) if E else None, 0)
     # gate MLP backward; its input gradient is accumulated onto the aggregation's d_msg
