@@ -93,6 +93,7 @@ def build_case(cfg_name, device, rank):
     from gcbf_b200 import synth
     from gcbf_b200.synth import seeded_algo
     c = dict(synth.CONFIGS[cfg_name])
+    c['num_graphs'] = synth.GRAPHS_PER_GPU[cfg_name]
     c['seed'] = c['seed'] + 7919 * rank            # every rank owns different graphs (environment-parallel)
     sb = synth.make_states(**c)
     env, algo = seeded_algo(sb.env, sb.num_agents, device, 0, {'num_obs': sb.num_obs, 'area_size': sb.area_size})
@@ -231,7 +232,7 @@ def cpu_sample_step(cfg_name, graphs):
 
 def cpu_baseline(cfg_name, budget_s=20.0):
     from gcbf_b200 import synth
-    full = synth.CONFIGS[cfg_name]['num_graphs']
+    full = synth.GRAPHS_PER_GPU[cfg_name]
     graphs = max(1, min(full, 4))
     step, sb = cpu_sample_step(cfg_name, graphs)
     step()                                       # warm-up
@@ -255,7 +256,7 @@ def run_reference(args):
     if rank != 0:
         return
     from gcbf_b200 import synth
-    full = synth.CONFIGS[args.config]['num_graphs']
+    full = synth.GRAPHS_PER_GPU[args.config]
     graphs = max(1, min(full, 4))
     step, sb = cpu_sample_step(args.config, graphs)
     for _ in range(min(args.warmup, 1)):

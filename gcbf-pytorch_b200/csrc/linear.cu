@@ -10,6 +10,13 @@ int launch_simt_dgrad(const float* dZ, int lddz, const float* W, int ldw, const 
                       cudaStream_t st);
 int launch_simt_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw,
                       float* db, int M, int N, int K, int accumulate, cudaStream_t st);
+bool skinny_supported(int K);
+int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
+                      int ldy, int M, int N, int K, int act, cudaStream_t st);
+int launch_skinny_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src,
+                        int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
+int launch_skinny_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw,
+                        float* db, int M, int N, int K, int accumulate, cudaStream_t st);
 #ifdef GCBF_WITH_TCGEN05
 bool tc_fwd_supported(int ldx, int ldw, int ldy, int M, int N, int K, bool forced);
 int launch_tc_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
@@ -49,6 +56,10 @@ extern "C" int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw,
     return launch_tc_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st); }
 #endif
   if (impl == 2) { set_error("gcbf_linear_fwd: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {   // K <= 16: HBM-bound stream, not a GEMM tile
+    g_last_impl = 3;
+    return launch_skinny_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
+  }
   g_last_impl = 1;
   return launch_simt_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
 }
@@ -66,6 +77,10 @@ extern "C" int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, i
     return launch_tc_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st); }
 #endif
   if (impl == 2) { set_error("gcbf_linear_bwd_data: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {
+    g_last_impl = 3;
+    return launch_skinny_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
+  }
   g_last_impl = 1;
   return launch_simt_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
 }
@@ -89,6 +104,10 @@ extern "C" int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X,
     return launch_tc_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st); }
 #endif
   if (impl == 2) { set_error("gcbf_linear_bwd_weight: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {
+    g_last_impl = 3;
+    return launch_skinny_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);
+  }
   g_last_impl = 1;
   return launch_simt_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);
 }

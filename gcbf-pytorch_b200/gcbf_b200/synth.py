@@ -87,6 +87,9 @@ CONFIGS = {
     'C4': dict(env='SimpleDrone', num_agents=1024, num_obs=1024, num_graphs=16, area_size=8.0, seed=1004),
     'C5': dict(env='DubinsCar', num_agents=4096, num_obs=128, num_graphs=8, area_size=16.0, seed=1005),
 }
+# graphs one GPU owns (bench.py is weak scaling: every rank gets this many).  C4 / C5 are defined over 8 GPUs in
+# BASELINE.json (16 replicas -> 2 per GPU, 8 dense graphs -> 1 per GPU); C1..C3 are single-GPU batches.
+GRAPHS_PER_GPU = {'C1': 1, 'C2': 32, 'C3': 64, 'C4': 2, 'C5': 1}
 
 
 def seeded_algo(env_name, n, device, init_seed=0, env_params=None, hyperparams='table'):

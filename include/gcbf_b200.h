@@ -43,7 +43,8 @@ const char* gcbf_last_error(void);
 int gcbf_abi_version(void);
 /* 1 if the library was built with the tcgen05 (3xTF32) GEMM path compiled in, else 0 */
 int gcbf_has_tcgen05(void);
-/* which kernel the most recent gcbf_linear_* call on this thread launched: 1 = fp32 SIMT, 2 = tcgen05 3xTF32 */
+/* which kernel the most recent gcbf_linear_* call on this thread launched: 1 = fp32 SIMT tile GEMM, 2 = tcgen05 3xTF32,
+ * 3 = fp32 skinny-K stream kernel (in-features <= 16) */
 int gcbf_last_gemm_impl(void);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -172,6 +172,31 @@ def test_linear_tcgen05_3xtf32(M, N, K):
     assert e(db, dz64.sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize('M,N,K', [(5000, 2048, 13), (129, 256, 12), (24196, 2048, 14), (1000, 70, 16), (64, 64, 1)])
+def test_linear_skinny_k(M, N, K):
+    """In-features <= 16 (first phi layer): dedicated HBM-streaming kernels, exact fp32 FFMA."""
+    g = _g(M + N + K)
+    x, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    dz, rs = torch.randn(M, N, generator=g), torch.randn(M, K, generator=g)
+    xd, Wd, bd, dzd, rsd = x.to(DEV), W.to(DEV), b.to(DEV), dz.to(DEV), rs.to(DEV)
+    alpha = torch.tensor([0.9], device=DEV)
+    assert ops.GEMM_IMPL == 0
+    y = ops.linear_fwd(xd, Wd, bd, alpha, ops.ACT_RELU)
+    assert _C.lib().gcbf_last_gemm_impl() == 3
+    dx = ops.linear_bwd_data(dzd, Wd, alpha, rsd)
+    dx_acc = torch.ones(M, K, device=DEV)
+    ops.linear_bwd_data(dzd, Wd, None, None, out=dx_acc, accumulate=True)
+    dW, db = ops.linear_bwd_weight(dzd, xd, alpha)
+    assert _C.lib().gcbf_last_gemm_impl() == 3
+    x64, W64, dz64 = xd.double(), Wd.double(), dzd.double()
+    e = lambda a, r: ((a.double() - r).abs().max() / r.abs().max()).item()
+    assert e(y, torch.relu(0.9 * (x64 @ W64.t()) + bd.double())) < 2e-6
+    assert e(dx, 0.9 * (dz64 @ W64) * (rsd > 0)) < 1e-5
+    assert e(dx_acc, dz64 @ W64 + 1) < 1e-5
+    assert e(dW, 0.9 * (dz64.t() @ x64)) < 1e-5
+    assert e(db, dz64.sum(0)) < 1e-5
+
+
 def test_linear_strided_views():
     """Kernels take leading dimensions: column slices of wider buffers must work without copies."""
     g = _g(9)
