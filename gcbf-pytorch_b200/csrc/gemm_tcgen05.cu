@@ -16,6 +16,7 @@
 //      3 x BK/8 tcgen05.mma per stage, accumulators double-buffered in TMEM), warps 2-5 = epilogue
 //      (tcgen05.ld 32x32b.x32 -> fused alpha/bias/activation | ReLU-mask | accumulate -> global).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -24,10 +25,15 @@ namespace gcbf {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                 // fp32 elements per k-block = 128 bytes = one swizzle-128B row
+#ifndef GCBF_TC_BK
+#define GCBF_TC_BK 16
+#endif
+constexpr int BK = GCBF_TC_BK;         // fp32 elements per k-block: 32 = 128 B rows (SWIZZLE_128B), 16 = 64 B rows (SWIZZLE_64B)
+constexpr int SWIZZLE_BYTES = BK * 4;  // one smem row of a tile == one swizzle span
+static_assert(BK == 16 || BK == 32, "BK must be 16 or 32");
 constexpr int UMMA_K = 8;              // tf32: 32 bytes per instruction
 constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 epilogue / fp32 chunk accumulation
-constexpr int KCH = 8;                 // k-blocks (of 32) accumulated inside the tensor core before promotion to registers
+constexpr int KCH = 256 / BK;          // k-blocks accumulated inside the tensor core (256 K-elements) before promotion to registers
 constexpr int MAX_CHUNK_ROWS = 65536;  // rows of the big operand processed per launch (bounds the scratch)
 
 enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
@@ -134,9 +140,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * SWIZZLE_BYTES) >> 4) << 32;   // stride between 8-row swizzle atoms
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(SWIZZLE_BYTES == 128 ? 2 : 4) << 61;  // SWIZZLE_128B = 2, SWIZZLE_64B = 4
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
@@ -145,9 +151,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- operand preparation: [hi; lo] split, optional transpose, zero padding -----------------------------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  const uint32_t b = __float_as_uint(x);
+  if ((b & 0x7f800000u) == 0x7f800000u) { hi = x; lo = 0.f; return; }   // inf / nan pass through
+  hi = __uint_as_float((b + 0x1000u) & 0xffffe000u);                     // round to nearest tf32 (10-bit mantissa)
+  lo = __fsub_rn(x, hi);                                                 // exact
+}
+
+// dst_hi[r][c] (r < R_pad, c < C_pad), element (r, c) = TRANS ? src[c][r] : src[r][c]; zero outside [rows, cols)
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int STAGES = ((BN == 256) ? 2 : 3) * (32 / BK);
   static constexpr int A_BYTES = BM * BK * 4;          // one of hi / lo
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -155,7 +170,10 @@ struct Cfg {
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator (power of two: 256 / 512)
 };
 
-template <int BN>
+// A_RAW = true: operand A is the caller's fp32 matrix itself (TMA straight from it, out-of-range rows / columns zero
+// filled); the epilogue warps split every landed 128x32 tile into hi (in place) and lo in shared memory before the MMA
+// warp may read it -- no [hi; lo] scratch copy of the big activation operand in HBM.
+template <int BN, bool A_RAW>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int a_lo_row,
                int b_lo_row, float* __restrict__ C, int ldc, int Mo, int No, int tiles_m, int tiles_n,
@@ -168,7 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty = bars + K::STAGES;         // [STAGES]  MMA -> TMA
   uint64_t* tfull = bars + 2 * K::STAGES;     // [2]       MMA -> epilogue
   uint64_t* tempty = bars + 2 * K::STAGES + 2;  // [2]     epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * K::STAGES + 4);
+  uint64_t* conv = bars + 2 * K::STAGES + 4;    // [STAGES] converters -> MMA (A_RAW only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * K::STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb0 = blockIdx.y * kblocks_per_split;
@@ -179,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 8); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * 32); }
     fence_barrier_init();
   }
@@ -203,9 +222,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + stage * K::STAGE_BYTES;
-            mbar_expect_tx(&full[stage], K::STAGE_BYTES);
+            mbar_expect_tx(&full[stage], A_RAW ? K::STAGE_BYTES - K::A_BYTES : K::STAGE_BYTES);
             tma_load_2d(st, &map_a, &full[stage], kb * BK, m0);
-            tma_load_2d(st + K::A_BYTES, &map_a, &full[stage], kb * BK, a_lo_row + m0);
+            if (!A_RAW) tma_load_2d(st + K::A_BYTES, &map_a, &full[stage], kb * BK, a_lo_row + m0);
             tma_load_2d(st + 2 * K::A_BYTES, &map_b, &full[stage], kb * BK, n0);
             tma_load_2d(st + 2 * K::A_BYTES + K::B_BYTES, &map_b, &full[stage], kb * BK, b_lo_row + n0);
             if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
@@ -230,7 +249,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
             const int kend = min(nkb, kc + KCH);
             for (int kb = kc; kb < kend; ++kb) {
-              mbar_wait(&full[stage], phase);
+              mbar_wait(&full[stage], phase);                 // TMA bytes (A and B) have landed
+              if (A_RAW) mbar_wait(&conv[stage], phase);      // ... and A has been split into hi / lo
               tcgen05_fence_after();
               const uint32_t st = smem_u32(smem + stage * K::STAGE_BYTES);
               const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + K::A_BYTES);
@@ -259,12 +279,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const float alpha = ep.alpha ? __ldg(ep.alpha) : 1.f;
       int buf = 0;
       uint32_t tphase[2] = {0, 0};
+      int cstage = 0;
+      uint32_t cphase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
         float acc[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) acc[j] = 0.f;
-        for (int kc = 0; kc < nkb; kc += KCH) {
+        const int nch = (nkb + KCH - 1) / KCH;
+        int promoted = 0;
+        // add the finished chunk sum of TMEM buffer `buf` into the register accumulators (round-to-nearest fp32)
+        auto promote = [&]() {
           mbar_wait(&tfull[buf], tphase[buf]);
           tcgen05_fence_after();
           const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + chalf * CH) + ((uint32_t)(lg * 32) << 16);
@@ -280,6 +305,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_arrive(&tempty[buf]);
           tphase[buf] ^= 1;
           buf ^= 1;
+          ++promoted;
+        };
+        if (A_RAW) {
+          // converter duty: split each landed A tile (16 KB = 1024 x 16 B; 256 threads x 4) into hi (in place) / lo
+          const int ct = (warp - 2) * 32 + lane;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full[cstage], cphase);
+            float4* a_hi = reinterpret_cast<float4*>(smem + cstage * K::STAGE_BYTES);
+            float4* a_lo = reinterpret_cast<float4*>(smem + cstage * K::STAGE_BYTES + K::A_BYTES);
+#pragma unroll
+            static_assert((K::A_BYTES / 16) % 256 == 0, "converter mapping");
+#pragma unroll
+            for (int q = 0; q < (K::A_BYTES / 16) / 256; ++q) {
+              const int idx = q * 256 + ct;
+              const float4 x = a_hi[idx];
+              float4 hi, lo;
+              split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
+              split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+              a_hi[idx] = hi;
+              a_lo[idx] = lo;
+            }
+            fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&conv[cstage]);
+            if (++cstage == K::STAGES) { cstage = 0; cphase ^= 1; }
+            // chunk c-1 is complete once the MMA warp is past k-block KCH*c - 1; drain it one block later
+            if (kb >= KCH + 1 && (kb - 1) % KCH == 0) promote();
+          }
+          while (promoted < nch) promote();
+        } else {
+          for (int c = 0; c < nch; ++c) promote();
         }
         const int row = m0 + lg * 32 + lane;
         if (row < Mo) {
@@ -337,15 +393,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-// ---- operand preparation: [hi; lo] split, optional transpose, zero padding -----------------------------------
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  const uint32_t b = __float_as_uint(x);
-  if ((b & 0x7f800000u) == 0x7f800000u) { hi = x; lo = 0.f; return; }   // inf / nan pass through
-  hi = __uint_as_float((b + 0x1000u) & 0xffffe000u);                     // round to nearest tf32 (10-bit mantissa)
-  lo = __fsub_rn(x, hi);                                                 // exact
-}
-
-// dst_hi[r][c] (r < R_pad, c < C_pad), element (r, c) = TRANS ? src[c][r] : src[r][c]; zero outside [rows, cols)
 constexpr int TRANS_STRIP = 16;   // column tiles (of 32) per block in the transposing split
 
 template <bool TRANS>
@@ -418,15 +465,16 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const float* base, int rows_total, int cols, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, int rows_total, int cols, int ld, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return GCBF_E_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows_total};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d box_rows=%d", (int)r, rows_total, cols, box_rows); return GCBF_E_CUDA; }
   return GCBF_OK;
@@ -435,6 +483,7 @@ static int make_map(CUtensorMap* map, const float* base, int rows_total, int col
 // process-wide (one process per GPU): autograd runs backward on its own thread, so this must not be thread_local
 static float* g_ws = nullptr;
 static size_t g_ws_bytes = 0;
+static bool g_a_raw = true;   // in-kernel split of operand A (GCBF_TC_A_RAW=0 in the environment disables it)
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -460,19 +509,20 @@ static int prep_operand(const Operand& op, int tile_rows, float* dst, int* R_pad
   return GCBF_OK;
 }
 
-template <int BN>
-static int launch_tiles(const float* a_scr, int RA, const float* b_scr, int RB, int Kp, float* C, int ldc, int Mo, int No,
-                        int splits, const EpiParams& ep, cudaStream_t st) {
+template <int BN, bool A_RAW>
+static int launch_tiles(const float* a_ptr, int a_rows, int a_cols, int a_ld, const float* b_scr, int RB, int Kp, float* C,
+                        int ldc, int Mo, int No, int splits, const EpiParams& ep, cudaStream_t st) {
   using K = Cfg<BN>;
   CUtensorMap ma, mb;
-  if (int rc = make_map(&ma, a_scr, 2 * RA, Kp, BM)) return rc;
-  if (int rc = make_map(&mb, b_scr, 2 * RB, Kp, BN)) return rc;
+  // A_RAW: the map covers the caller's [Mo, Kc] matrix (OOB -> 0); otherwise the [hi; lo] scratch of 2*RA padded rows
+  if (int rc = make_map(&ma, a_ptr, A_RAW ? a_rows : 2 * a_rows, A_RAW ? a_cols : Kp, a_ld, BM)) return rc;
+  if (int rc = make_map(&mb, b_scr, 2 * RB, Kp, Kp, BN)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    GCBF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    GCBF_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles_m = RA / BM, tiles_n = RB / BN;
+  const int tiles_m = ceil_div(Mo, BM), tiles_n = RB / BN;
   const int kblocks = Kp / BK;
   const int kps = ceil_div(kblocks, splits);
   const int nsplit = ceil_div(kblocks, kps);
@@ -481,7 +531,8 @@ static int launch_tiles(const float* a_scr, int RA, const float* b_scr, int RB, 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ctas = max(1, min(tiles_m * tiles_n, max(1, sms / nsplit)));
   dim3 grid(ctas, nsplit);
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, K::SMEM_BYTES, st>>>(ma, mb, RA, RB, C, ldc, Mo, No, tiles_m, tiles_n, kps, kblocks, ep);
+  gemm_tc_kernel<BN, A_RAW><<<grid, NUM_THREADS, K::SMEM_BYTES, st>>>(ma, mb, a_rows, RB, C, ldc, Mo, No, tiles_m, tiles_n, kps,
+                                                                      kblocks, ep);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }
@@ -491,6 +542,15 @@ static int run_gemm(Operand A, Operand B, float* C, int ldc, EpiParams ep, bool 
   const int Mo = A.rows, No = B.rows, Kc = A.cols;
   const int BN = (No > 128) ? 256 : 128;
   if (!g_ws) { set_error("tcgen05 GEMM: no workspace registered (gcbf_set_gemm_workspace)"); return GCBF_E_INVALID; }
+  if (!chunk_k && !A.trans && (A.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(A.src) & 15) == 0 && g_a_raw) {
+    // operand A straight from the caller's matrix, split into hi / lo inside the kernel: only B needs scratch
+    const size_t need = operand_bytes(No, Kc, BN);
+    if (need > g_ws_bytes) { set_error("tcgen05 GEMM: workspace too small (%zu > %zu)", need, g_ws_bytes); return GCBF_E_INVALID; }
+    int RB, Kp;
+    if (int rc = prep_operand(B, BN, g_ws, &RB, &Kp, st)) return rc;
+    return (BN == 256) ? launch_tiles<256, true>(A.src, Mo, Kc, A.ld, g_ws, RB, Kp, C, ldc, Mo, No, 1, ep, st)
+                       : launch_tiles<128, true>(A.src, Mo, Kc, A.ld, g_ws, RB, Kp, C, ldc, Mo, No, 1, ep, st);
+  }
   if (!chunk_k) {
     for (int m0 = 0; m0 < Mo; m0 += MAX_CHUNK_ROWS) {
       const int mc = min(MAX_CHUNK_ROWS, Mo - m0);
@@ -506,8 +566,8 @@ static int run_gemm(Operand A, Operand B, float* C, int ldc, EpiParams ep, bool 
       if (int rc = prep_operand(B, BN, b_scr, &RB, &Kp2, st)) return rc;
       EpiParams e = ep;
       if (e.relu_src) e.relu_src = ep.relu_src + (size_t)m0 * ep.ld_relu;
-      int rc = (BN == 256) ? launch_tiles<256>(a_scr, RA, b_scr, RB, Kp, C + (size_t)m0 * ldc, ldc, mc, No, 1, e, st)
-                           : launch_tiles<128>(a_scr, RA, b_scr, RB, Kp, C + (size_t)m0 * ldc, ldc, mc, No, 1, e, st);
+      int rc = (BN == 256) ? launch_tiles<256, false>(a_scr, RA, Kp, Kp, b_scr, RB, Kp, C + (size_t)m0 * ldc, ldc, mc, No, 1, e, st)
+                           : launch_tiles<128, false>(a_scr, RA, Kp, Kp, b_scr, RB, Kp, C + (size_t)m0 * ldc, ldc, mc, No, 1, e, st);
       if (rc) return rc;
     }
     return GCBF_OK;
@@ -529,13 +589,13 @@ static int run_gemm(Operand A, Operand B, float* C, int ldc, EpiParams ep, bool 
     if (int rc = prep_operand(b, BN, b_scr, &RB, &Kp2, st)) return rc;
     const int tiles = (RA / BM) * (RB / BN);
     int splits = 1;
-    if (tiles < kNumSMs) splits = max(1, min(Kp / BK / 8, kNumSMs / tiles));
+    if (tiles < kNumSMs) splits = max(1, min(Kp / 256, kNumSMs / tiles));
     EpiParams e = ep;
     e.atomic = splits > 1;
     if (!first) e.accumulate = 1;
     if (e.atomic && !e.accumulate) GCBF_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)No * 4, Mo, st));
-    int rc = (BN == 256) ? launch_tiles<256>(a_scr, RA, b_scr, RB, Kp, C, ldc, Mo, No, splits, e, st)
-                         : launch_tiles<128>(a_scr, RA, b_scr, RB, Kp, C, ldc, Mo, No, splits, e, st);
+    int rc = (BN == 256) ? launch_tiles<256, false>(a_scr, RA, Kp, Kp, b_scr, RB, Kp, C, ldc, Mo, No, splits, e, st)
+                         : launch_tiles<128, false>(a_scr, RA, Kp, Kp, b_scr, RB, Kp, C, ldc, Mo, No, splits, e, st);
     if (rc) return rc;
     first = false;
   }
@@ -582,6 +642,8 @@ int launch_tc_wgrad(const float* dZ, int lddz, const float* X, int ldx, const fl
 }  // namespace gcbf
 
 extern "C" int gcbf_set_gemm_workspace(void* ptr, size_t bytes) {
+  const char* e = getenv("GCBF_TC_A_RAW");
+  gcbf::tc::g_a_raw = !(e && e[0] == '0');
   gcbf::tc::g_ws = reinterpret_cast<float*>(ptr);
   gcbf::tc::g_ws_bytes = ptr ? bytes : 0;
   return GCBF_OK;
