@@ -34,6 +34,10 @@ static_assert(BK == 16 || BK == 32, "BK must be 16 or 32");
 constexpr int UMMA_K = 8;              // tf32: 32 bytes per instruction
 constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 epilogue / fp32 chunk accumulation
 constexpr int KCH = 256 / BK;          // k-blocks accumulated inside the tensor core (256 K-elements) before promotion to registers
+#ifndef GCBF_TC_CONV_GROUPS
+#define GCBF_TC_CONV_GROUPS 4
+#endif
+constexpr int CONV_GROUPS = GCBF_TC_CONV_GROUPS;   // epilogue warps form this many converter groups taking k-blocks round robin
 constexpr int MAX_CHUNK_ROWS = 65536;  // rows of the big operand processed per launch (bounds the scratch)
 
 enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
@@ -47,6 +51,7 @@ struct EpiParams {
   int ld_relu;
   int accumulate;
   int atomic;
+  int dbg;   // experiment switches (GCBF_TC_DBG): 1 = converters skip the split, 2 = write lo only
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -198,7 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 8); }
+    for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 8 / CONV_GROUPS); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * 32); }
     fence_barrier_init();
   }
@@ -279,8 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const float alpha = ep.alpha ? __ldg(ep.alpha) : 1.f;
       int buf = 0;
       uint32_t tphase[2] = {0, 0};
-      int cstage = 0;
-      uint32_t cphase = 0;
+      uint32_t gk_base = 0;   // k-blocks this CTA has consumed so far (all tiles): stage = gk % STAGES
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
         float acc[CH];
@@ -308,31 +312,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           ++promoted;
         };
         if (A_RAW) {
-          // converter duty: split each landed A tile (16 KB = 1024 x 16 B; 256 threads x 4) into hi (in place) / lo
-          const int ct = (warp - 2) * 32 + lane;
+          // converter duty: split each landed A tile into hi (in place) and lo.  The 8 warps work as CONV_GROUPS groups
+          // that take k-blocks round robin (each group has CONV_GROUPS MMA k-block periods per tile it converts); addressing is
+          // explicit shared-space PTX (16-byte chunks, consecutive threads -> consecutive chunks: conflict free).
+          constexpr int GT = 256 / CONV_GROUPS;                        // threads per converter group
+          const int grp = (warp - 2) / (GT / 32);
+          const int gt = ((warp - 2) % (GT / 32)) * 32 + lane;         // 0..GT-1 inside the group
+          constexpr int CHUNKS = K::A_BYTES / 16;                      // 16-byte chunks per A tile
+          static_assert(CHUNKS % GT == 0, "converter mapping");
           for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&full[cstage], cphase);
-            float4* a_hi = reinterpret_cast<float4*>(smem + cstage * K::STAGE_BYTES);
-            float4* a_lo = reinterpret_cast<float4*>(smem + cstage * K::STAGE_BYTES + K::A_BYTES);
+            const uint32_t gk = gk_base + (uint32_t)kb;
+            if ((int)(gk % (uint32_t)CONV_GROUPS) == grp) {
+              const int cs = (int)(gk % (uint32_t)K::STAGES);
+              mbar_wait(&full[cs], (gk / (uint32_t)K::STAGES) & 1u);
+              const uint32_t a_hi = smem_u32(smem + cs * K::STAGE_BYTES);
+              if (!(ep.dbg & 1)) {
 #pragma unroll
-            static_assert((K::A_BYTES / 16) % 256 == 0, "converter mapping");
-#pragma unroll
-            for (int q = 0; q < (K::A_BYTES / 16) / 256; ++q) {
-              const int idx = q * 256 + ct;
-              const float4 x = a_hi[idx];
-              float4 hi, lo;
-              split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
-              split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-              a_hi[idx] = hi;
-              a_lo[idx] = lo;
+                for (int q = 0; q < CHUNKS / GT; ++q) {
+                  const uint32_t addr = a_hi + (uint32_t)((q * GT + gt) * 16);
+                  uint32_t x0, x1, x2, x3;
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+                  const uint32_t h0 = (x0 + 0x1000u) & 0xffffe000u, h1 = (x1 + 0x1000u) & 0xffffe000u;
+                  const uint32_t h2 = (x2 + 0x1000u) & 0xffffe000u, h3 = (x3 + 0x1000u) & 0xffffe000u;
+                  const uint32_t l0 = __float_as_uint(__fsub_rn(__uint_as_float(x0), __uint_as_float(h0)));
+                  const uint32_t l1 = __float_as_uint(__fsub_rn(__uint_as_float(x1), __uint_as_float(h1)));
+                  const uint32_t l2 = __float_as_uint(__fsub_rn(__uint_as_float(x2), __uint_as_float(h2)));
+                  const uint32_t l3 = __float_as_uint(__fsub_rn(__uint_as_float(x3), __uint_as_float(h3)));
+                  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+                  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr + (uint32_t)K::A_BYTES), "r"(l0), "r"(l1), "r"(l2), "r"(l3)
+                               : "memory");
+                }
+              }
+              fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&conv[cs]);
             }
-            fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&conv[cstage]);
-            if (++cstage == K::STAGES) { cstage = 0; cphase ^= 1; }
-            // chunk c-1 is complete once the MMA warp is past k-block KCH*c - 1; drain it one block later
-            if (kb >= KCH + 1 && (kb - 1) % KCH == 0) promote();
+            // chunk c is complete once the MMA warp is past k-block KCH*(c+1) - 1; by the time this warp sees k-block
+            // KCH*(c+1) + STAGES the MMA warp has released that block's stage, so the wait below does not stall
+            if (kb >= KCH + K::STAGES && (kb - K::STAGES) % KCH == 0) promote();
           }
+          gk_base += (uint32_t)nkb;
           while (promoted < nch) promote();
         } else {
           for (int c = 0; c < nch; ++c) promote();
@@ -348,21 +367,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = alpha * acc[c * 32 + j];
+            const bool full32 = (nv == 32);
             if (ep.mode == EPI_FWD) {
+              float bv[32];
+              if (ep.bias && full32 && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                  bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) bv[j] = (ep.bias && j < nv) ? __ldg(ep.bias + col0 + j) : 0.f;
+              }
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                if (j < nv) {
-                  float y = v[j] + (ep.bias ? __ldg(ep.bias + col0 + j) : 0.f);
-                  if (ep.act == GCBF_ACT_RELU) y = fmaxf(y, 0.f);
-                  else if (ep.act == GCBF_ACT_TANH) y = tanhf(y);
-                  v[j] = y;
-                }
+                float y = v[j] + bv[j];
+                if (ep.act == GCBF_ACT_RELU) y = fmaxf(y, 0.f);
+                else if (ep.act == GCBF_ACT_TANH) y = tanhf(y);
+                v[j] = y;
               }
             } else if (ep.mode == EPI_DGRAD && ep.relu_src) {
               const float* ms = ep.relu_src + (size_t)row * ep.ld_relu + col0;
+              if (full32 && ((reinterpret_cast<uintptr_t>(ms) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) v[j] = (__ldg(ms + j) > 0.f) ? v[j] : 0.f;
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 m4 = __ldg(reinterpret_cast<const float4*>(ms + j));
+                  v[j] = m4.x > 0.f ? v[j] : 0.f; v[j + 1] = m4.y > 0.f ? v[j + 1] : 0.f;
+                  v[j + 2] = m4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = m4.w > 0.f ? v[j + 3] : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) v[j] = (__ldg(ms + j) > 0.f) ? v[j] : 0.f;
+              }
             }
             if (ep.mode == EPI_WGRAD && ep.atomic) {
 #pragma unroll
@@ -483,6 +521,7 @@ static int make_map(CUtensorMap* map, const float* base, int rows_total, int col
 // process-wide (one process per GPU): autograd runs backward on its own thread, so this must not be thread_local
 static float* g_ws = nullptr;
 static size_t g_ws_bytes = 0;
+static int g_dbg = 0;
 static bool g_a_raw = true;   // in-kernel split of operand A (GCBF_TC_A_RAW=0 in the environment disables it)
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -548,6 +587,7 @@ static int run_gemm(Operand A, Operand B, float* C, int ldc, EpiParams ep, bool 
     if (need > g_ws_bytes) { set_error("tcgen05 GEMM: workspace too small (%zu > %zu)", need, g_ws_bytes); return GCBF_E_INVALID; }
     int RB, Kp;
     if (int rc = prep_operand(B, BN, g_ws, &RB, &Kp, st)) return rc;
+    ep.dbg = g_dbg;
     return (BN == 256) ? launch_tiles<256, true>(A.src, Mo, Kc, A.ld, g_ws, RB, Kp, C, ldc, Mo, No, 1, ep, st)
                        : launch_tiles<128, true>(A.src, Mo, Kc, A.ld, g_ws, RB, Kp, C, ldc, Mo, No, 1, ep, st);
   }
@@ -644,6 +684,8 @@ int launch_tc_wgrad(const float* dZ, int lddz, const float* X, int ldx, const fl
 extern "C" int gcbf_set_gemm_workspace(void* ptr, size_t bytes) {
   const char* e = getenv("GCBF_TC_A_RAW");
   gcbf::tc::g_a_raw = !(e && e[0] == '0');
+  const char* d = getenv("GCBF_TC_DBG");
+  gcbf::tc::g_dbg = d ? atoi(d) : 0;
   gcbf::tc::g_ws = reinterpret_cast<float*>(ptr);
   gcbf::tc::g_ws_bytes = ptr ? bytes : 0;
   return GCBF_OK;
