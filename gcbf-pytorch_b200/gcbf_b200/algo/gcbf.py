@@ -229,6 +229,51 @@ class GCBF(Algorithm):
         self.buffer.clear()
         return info
 
+    # ---- test-time controller -------------------------------------------------------
+    def apply(self, data, rand: Optional[float] = 30, max_iter: int = 30) -> Tensor:
+        """Reference gcbf.py:260-309 for ONE graph: keep the actor's action only where the nominal (zero) action
+        violates the h_dot condition, then up to max_iter+1 per-agent Adam(lr=0.1) steps on the violating agents'
+        actions through forward_graph -> CBF (same kernels as training: K2, K3, K4, K5 forward and input-gradient),
+        plus the reference's gradient noise `rand * lr * randn * grad`.  The per-agent optimisers are kept as one
+        vectorised state (m, v, step count per agent); the O(num_agents) arithmetic around the kernels is host glue."""
+        env, alpha, lr = self._env, float(self.params['alpha']), 0.1
+        dt = float(env.dt)
+        with torch.no_grad():
+            h = self.cbf(data)
+            action = self.actor(data)
+            nominal = torch.zeros_like(action)
+            h_next = self.cbf(env.forward_graph(data, nominal))
+            viol = torch.relu(-(h_next - h) / dt - alpha * h).reshape(-1)
+            act = torch.where((viol <= 0).unsqueeze(1), nominal, action).clone()
+        m, v = torch.zeros_like(act), torch.zeros_like(act)
+        t = torch.zeros(act.shape[0], device=act.device)
+        it = 0
+        while True:
+            a = act.clone().requires_grad_(True)
+            h_next = self.cbf(env.forward_graph(data, a))
+            max_val = torch.relu(-(h_next - h) / dt - alpha * h)
+            loss = torch.mean(max_val)
+            if float(loss.detach()) <= 0 or it > max_iter:
+                return a.detach()
+            sel = (max_val.detach().reshape(-1) != 0)
+            from .. import ops
+            ops.SKIP_WGRAD = True           # only d loss / d action is needed: skip every weight-gradient GEMM
+            try:
+                (g,) = torch.autograd.grad(loss, a)
+            finally:
+                ops.SKIP_WGRAD = False
+            with torch.no_grad():
+                s2 = sel.unsqueeze(1)
+                t = torch.where(sel, t + 1, t)
+                m = torch.where(s2, m + (g - m) * (1 - 0.9), m)
+                v = torch.where(s2, v * 0.999 + (1 - 0.999) * g * g, v)
+                bc1 = (1 - 0.9 ** t).clamp(min=1e-30).unsqueeze(1)
+                bc2 = (1 - 0.999 ** t).clamp(min=1e-30).unsqueeze(1)
+                act = torch.where(s2, act - (lr / bc1) * m / (v.sqrt() / bc2.sqrt() + 1e-8), act)
+                if rand:
+                    act = torch.where(s2, act - rand * lr * torch.randn_like(g) * g, act)
+            it += 1
+
     # ---- checkpoints (file names and keys of gcbf.py:249-258) ------------------------------------------
     def save(self, save_dir: str):
         os.makedirs(save_dir, exist_ok=True)

@@ -322,6 +322,9 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool) -> Tu
     return x, ctx
 
 
+SKIP_WGRAD = False   # set by GCBF.apply: only input gradients are needed there, weight-gradient GEMMs are skipped
+
+
 def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, need_dx: bool,
                  dx_out: Optional[torch.Tensor] = None, dx_accumulate: bool = False):
     """Returns (dx or None, [(dW, db) per layer])."""
@@ -336,11 +339,14 @@ def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, ne
         L = layers[l]
         x_in = ctx.acts[l]
         inv_sigma = ctx.inv_sigma[l]
-        dW, db = linear_bwd_weight(dz, x_in, inv_sigma)
-        if L.sn:
-            u, v = ctx.uv[l]
-            sn_grad_fixup(dW, L.W, u, v, inv_sigma)
-        grads[l] = (dW, db)
+        if SKIP_WGRAD:
+            grads[l] = (None, None)
+        else:
+            dW, db = linear_bwd_weight(dz, x_in, inv_sigma)
+            if L.sn:
+                u, v = ctx.uv[l]
+                sn_grad_fixup(dW, L.W, u, v, inv_sigma)
+            grads[l] = (dW, db)
         if l > 0:
             # hidden ReLU of layer l-1 folded into the epilogue: dz_{l-1} = (dz_l W_l) * (y_{l-1} > 0)
             assert layers[l - 1].act == ACT_RELU

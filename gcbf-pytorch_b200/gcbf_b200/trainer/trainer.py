@@ -52,8 +52,7 @@ class Trainer:
         print(f'> Done in {time() - start:.0f} seconds')
 
     def eval(self, step: int, eval_epi: int) -> Tuple[float, dict]:
-        """Nominal-free rollouts of the current actor (the reference evaluates `algo.apply`, its test-time
-        refinement, trainer.py:95-141; that path is listed as "next" in SURVEY section 8f)."""
+        """Rollouts with the test-time controller `algo.apply` (reference trainer.py:95-141)."""
         rewards, safes = [], []
         self.algo._env = self.env_test
         for _ in range(eval_epi):
@@ -61,8 +60,7 @@ class Trainer:
             ep_reward, ep_safe, t = 0., [], 0
             while True:
                 data.update(Data(u_ref=self.env_test.u_ref(data)))
-                with torch.no_grad():
-                    action = self.algo.act(data)
+                action = self.algo.apply(data)
                 data, reward, done, info = self.env_test.step(action)
                 ep_reward += float(np.mean(reward))
                 ep_safe.append(info['safe'])

@@ -46,7 +46,7 @@ def main():
             states=sb.states, goals=sb.goals,
             edge_index=res['edge_index'], u_ref=res['u_ref'], edge_attr=res['edge_attr'],
             h_probe=res['h_probe'], u_probe=res['u_probe'], unsafe_mask=res['unsafe_mask'],
-            safe_mask=res['safe_mask'], states_next_probe=res['states_next_probe'],
+            safe_mask=res['safe_mask'], states_next_probe=res['states_next_probe'], apply_action=res['apply_action'],
             steps=res['steps'], cbf_init=digest(res['cbf_init']), actor_init=digest(res['actor_init']),
             cbf_final=digest(res['cbf_final']), actor_final=digest(res['actor_final']),
         )

@@ -100,6 +100,10 @@ def run_reference(sb, init_seed=0, pretrained=None, n_steps=1):
         out['safe_mask'] = env.safe_mask(batch).clone()
         nxt = env.forward_graph(batch, out['u_probe'])
         out['states_next_probe'] = nxt.states.clone()
+    # --- test-time controller on the first graph (noise off: rand=0) ---------------------------------
+    algo_c = copy.deepcopy(algo)
+    algo_c._env = env
+    out['apply_action'] = algo_c.apply(graphs[0], rand=0).detach().clone()
     # --- the real train step(s) ----------------------------------------------------------------------
     algo.params['inner_iter'] = 1
     algo.buffer.sample = lambda *a, **k: list(graphs)

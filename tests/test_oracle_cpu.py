@@ -64,6 +64,24 @@ def test_port_matches_golden(case):
     assert not digest_close(r['actor'], fix['actor_final'], 1e-6, 1e-6)
 
 
+@pytest.mark.parametrize('case', ['dubins_n16_o4_b3', 'simplecar_c1', 'drone_n8_b2'])
+def test_port_apply_matches_golden(case):
+    """GCBF.apply (test-time controller, noise off) of the port against the reference's own apply()."""
+    fix = load_golden(case)
+    meta = fix['meta']
+    sb = case_inputs(meta)
+    _, algo = seeded_algo(sb.env, sb.num_agents, torch.device('cpu'), meta['init_seed'],
+                          {'num_obs': sb.num_obs, 'area_size': sb.area_size})
+    cbf, act = sd_clone(algo.cbf), sd_clone(algo.actor)
+    ob = oracle_batch(sb)
+    n, N = sb.num_agents, sb.nodes_per_graph
+    ei0 = ob['edge_index'][:, ob['edge_index'][1] < N]
+    a, it = O.apply_controller(sb.env, cbf, act, sb.states[:N], sb.goals, ei0, ob['u_ref'][:n], n, sb.num_obs,
+                               O.HYPERPARAMS[sb.env]['alpha'], K=ob['K'])
+    assert it >= 1
+    assert torch.allclose(a, fix['apply_action'], rtol=1e-4, atol=1e-4), (a - fix['apply_action']).abs().max()
+
+
 @pytest.mark.skipif(not has_ref, reason='reference checkout not present (GPU box)')
 @pytest.mark.parametrize('cfg', [('SimpleCar', 12, 0, 2, 2.0), ('DubinsCar', 10, 3, 2, 2.0), ('SimpleDrone', 6, 6, 2, 1.0)])
 def test_port_matches_live_reference(cfg, tmp_path):
