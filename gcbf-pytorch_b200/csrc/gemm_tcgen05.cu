@@ -332,13 +332,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   const uint32_t addr = a_hi + (uint32_t)((q * GT + gt) * 16);
                   uint32_t x0, x1, x2, x3;
                   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
-                  const uint32_t h0 = (x0 + 0x1000u) & 0xffffe000u, h1 = (x1 + 0x1000u) & 0xffffe000u;
-                  const uint32_t h2 = (x2 + 0x1000u) & 0xffffe000u, h3 = (x3 + 0x1000u) & 0xffffe000u;
+                  const uint32_t rnd = (ep.dbg & 4) ? 0u : 0x1000u;   // dbg 4: truncate (what the tensor core would do to raw x)
+                  const uint32_t h0 = (x0 + rnd) & 0xffffe000u, h1 = (x1 + rnd) & 0xffffe000u;
+                  const uint32_t h2 = (x2 + rnd) & 0xffffe000u, h3 = (x3 + rnd) & 0xffffe000u;
                   const uint32_t l0 = __float_as_uint(__fsub_rn(__uint_as_float(x0), __uint_as_float(h0)));
                   const uint32_t l1 = __float_as_uint(__fsub_rn(__uint_as_float(x1), __uint_as_float(h1)));
                   const uint32_t l2 = __float_as_uint(__fsub_rn(__uint_as_float(x2), __uint_as_float(h2)));
                   const uint32_t l3 = __float_as_uint(__fsub_rn(__uint_as_float(x3), __uint_as_float(h3)));
-                  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
+                  if (!(ep.dbg & 4))
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(h0), "r"(h1), "r"(h2), "r"(h3) : "memory");
                   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr + (uint32_t)K::A_BYTES), "r"(l0), "r"(l1), "r"(l2), "r"(l3)
                                : "memory");
                 }
