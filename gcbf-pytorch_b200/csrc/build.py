@@ -30,7 +30,7 @@ def build(force=False, verbose=True):
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
     defs = []
-    if os.path.exists(os.path.join(HERE, 'gemm_tcgen05.cu')):
+    if os.path.exists(os.path.join(HERE, 'gemm_tcgen05_f16.cu')):
         defs.append('-DGCBF_WITH_TCGEN05')
     procs = []
     objs = []

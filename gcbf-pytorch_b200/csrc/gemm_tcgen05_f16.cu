@@ -1,0 +1,563 @@
+// tcgen05 GEMM with error-compensated 3xFP16 arithmetic -- the fast path of the linear layers of gcbf.nn.MLP
+// (reference gcbf/nn/mlp.py:44-47; the 2048-wide phi / gamma GEMMs are > 99 % of the FLOPs of a GCBF.update step).
+//
+// Precision.  The parity bar (h, u, loss within 1e-5 of the fp32 reference) rules out plain TF32 / bf16 / fp16 operands.
+// Every fp32 operand x is scaled by a per-tensor power of two s (max|x|*s in [2^14, 2^15), exact) and split
+//        x*s = hi + lo,   hi = fp16(x*s),   lo = fp16(x*s - hi)            (22 significand bits together)
+// and a product is accumulated in fp32 TMEM as  hi*hi + lo*hi + hi*lo  (3 tcgen05.mma.kind::f16 per k-slice; lo*lo ~ 2^-22
+// is dropped) and descaled by 1/(s_a*s_b) in the epilogue.  Same 22-bit operand precision as a 3xTF32 scheme at twice the
+// tensor-core rate (kind::f16 consumes 16 K-elements per instruction, kind::tf32 8).  Elements more than 2^17 below the
+// tensor's max lose relative (not absolute) precision: their absolute error stays <= 2^-39 of the max.
+//
+// "Split once, use everywhere".  The [hi | lo] fp16 companion of a matrix has the *same row-major layout* as the matrix,
+// and the tensor core takes either operand K-major or MN-major, so one companion serves every GEMM the matrix is in:
+//        forward      Y  = X  * W^T     A = X  (K-major)     B = W  (K-major)
+//        data-grad    dX = dZ * W       A = dZ (K-major)     B = W  (MN-major)
+//        weight-grad  dW = dZ^T * X     A = dZ (MN-major)    B = X  (MN-major)
+// No transposes, no padding copies: TMA zero-fills ragged edges of the exact-size tensor maps.
+//
+// Kernel.  Persistent CTAs (grid = #SMs), warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor 2-D boxes into
+// swizzled shared memory, 4 stages x 48 KB), warp 1 = MMA issuer (one thread; 6 tcgen05.mma M128 N256 K16 per stage;
+// accumulators double-buffered in 512 TMEM columns), warps 2-9 = chunk promotion + epilogue.  The tensor core's fp32
+// accumulator truncates on every MMA (tools/acc_probe.py), so K is consumed in chunks of 256: each chunk accumulates in
+// a fresh TMEM buffer and the epilogue warps add the chunk sums in registers with round-to-nearest.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tcgen05_ptx.cuh"
+
+namespace gcbf {
+namespace th {
+
+using namespace ptx;
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // K elements per k-block (= one smem stage)
+constexpr int UMMA_K = 16;             // fp16: 32 bytes of K per instruction
+constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 promotion / epilogue
+constexpr int KCH = 256 / BK;          // k-blocks accumulated inside the tensor core before promotion to registers
+constexpr int MN_BOX = 64;             // MN-major operands: one TMA box = 64 MN elements (128 B, SWIZZLE_128B) x BK k-rows
+
+enum { EPI_FWD = 0, EPI_DGRAD = 1, EPI_WGRAD = 2 };
+
+struct EpiParams {
+  int mode;
+  const float* alpha;          // device scalar (1/sigma of the spectral norm) or null
+  const float* bias;
+  int act;
+  const float* relu_src;
+  int ld_relu;
+  int accumulate;
+  int atomic;
+  const uint32_t* amax_a;      // device: float bits of max|A|, max|B| (the scales the companions were made with)
+  const uint32_t* amax_b;
+  uint32_t* amax_out;          // optional: atomicMax of |output| (feeds the next layer's split), or null
+};
+
+// power-of-two scale s with amax*s in [2^14, 2^15); 1 for zero / denormal / non-finite amax
+__host__ __device__ __forceinline__ uint32_t scale_bits_from_amax(uint32_t amax_bits) {
+  const int e = (int)((amax_bits >> 23) & 0xffu);
+  if (e == 0 || e == 255) return 0x3f800000u;
+  int se = 127 + 14 - (e - 127);
+  se = se < 2 ? 2 : (se > 252 ? 252 : se);
+  return (uint32_t)se << 23;
+}
+__host__ __device__ __forceinline__ uint32_t inv_pow2_bits(uint32_t s_bits) { return (uint32_t)(254 - (int)(s_bits >> 23)) << 23; }
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;          // one of hi / lo
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator (256 / 512 columns)
+};
+
+// descriptor of the k-slice `kk` (16 K-elements) of an operand tile in shared memory
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t tile_desc(uint32_t tile_addr, int kk) {
+  if (MN_MAJOR) {
+    // [MN/64 boxes][BK k-rows][64 MN elements]: 8 k-rows x 128 B = one swizzle atom; k-groups 1024 B apart (SBO),
+    // 64-wide MN atoms BK*128 B apart (LBO)
+    return make_smem_desc(tile_addr + (uint32_t)(kk * UMMA_K * 128), BK * 128, 1024, 128);
+  }
+  // [rows][BK k-elements] = 64-byte rows, SWIZZLE_64B: 8-row atoms 512 B apart (SBO); +32 B per k-slice inside the row
+  return make_smem_desc(tile_addr + (uint32_t)(kk * UMMA_K * 2), 16, 8 * BK * 2, BK * 2);
+}
+
+template <bool MN_MAJOR>
+__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int mn0, int k0, int rows) {
+  if (MN_MAJOR) {
+    for (int j = 0; j < rows / MN_BOX; ++j) tma_load_2d(dst + j * (BK * 128), map, bar, mn0 + j * MN_BOX, k0);
+  } else {
+    tma_load_2d(dst, map, bar, k0, mn0);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C,
+              int ldc, int Mo, int No, int tiles_m, int tiles_n, int kblocks_per_split, int kblocks_total, EpiParams ep) {
+  using K = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::STAGES * K::STAGE_BYTES);
+  uint64_t* full = bars;                        // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + K::STAGES;           // [STAGES]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * K::STAGES;       // [2]       MMA -> epilogue
+  uint64_t* tempty = bars + 2 * K::STAGES + 2;  // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * K::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb0 = blockIdx.y * kblocks_per_split;
+  const int kb1 = min(kblocks_total, kb0 + kblocks_per_split);
+  const int nkb = kb1 - kb0;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_a_lo);
+    tma_prefetch_desc(&map_b_hi);
+    tma_prefetch_desc(&map_b_lo);
+    for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * 32); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {            // one warp allocates TMEM and later frees it
+    tmem_alloc(tmem_slot, K::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      // ===== TMA producer =====
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+          const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* st = smem + stage * K::STAGE_BYTES;
+            mbar_expect_tx(&full[stage], K::STAGE_BYTES);
+            load_tile<A_MN>(st, &map_a_hi, &full[stage], m0, kb * BK, BM);
+            load_tile<A_MN>(st + K::A_BYTES, &map_a_lo, &full[stage], m0, kb * BK, BM);
+            load_tile<B_MN>(st + 2 * K::A_BYTES, &map_b_hi, &full[stage], n0, kb * BK, BN);
+            load_tile<B_MN>(st + 2 * K::A_BYTES + K::B_BYTES, &map_b_lo, &full[stage], n0, kb * BK, BN);
+            if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer (single thread) =====
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_f16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int buf = 0;
+        uint32_t tphase[2] = {0, 0};
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+          for (int kc = 0; kc < nkb; kc += KCH) {
+            mbar_wait(&tempty[buf], tphase[buf] ^ 1);        // epilogue has drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+            const int kend = min(nkb, kc + KCH);
+            for (int kb = kc; kb < kend; ++kb) {
+              mbar_wait(&full[stage], phase);                 // TMA bytes have landed
+              tcgen05_fence_after();
+              const uint32_t st = smem_u32(smem + stage * K::STAGE_BYTES);
+              const uint32_t a_hi = st, a_lo = st + K::A_BYTES, b_hi = st + 2 * K::A_BYTES, b_lo = st + 2 * K::A_BYTES + K::B_BYTES;
+#pragma unroll
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                const uint64_t dah = tile_desc<A_MN>(a_hi, kk), dal = tile_desc<A_MN>(a_lo, kk);
+                const uint64_t dbh = tile_desc<B_MN>(b_hi, kk), dbl = tile_desc<B_MN>(b_lo, kk);
+                umma_f16(d_tmem, dal, dbh, idesc, (kb > kc || kk > 0) ? 1u : 0u);
+                umma_f16(d_tmem, dah, dbl, idesc, 1u);
+                umma_f16(d_tmem, dah, dbh, idesc, 1u);
+              }
+              umma_commit(&empty[stage]);                     // smem slot free once these MMAs retire
+              if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tfull[buf]);                          // chunk sum complete -> epilogue
+            tphase[buf] ^= 1;
+            buf ^= 1;
+          }
+        }
+      }
+    } else {
+      // ===== promotion / epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+      constexpr int CH = BN / 2;                               // columns owned by one thread
+      const int lg = warp & 3;
+      const int chalf = (warp - 2) >> 2;
+      const uint32_t sa = scale_bits_from_amax(__ldg(ep.amax_a)), sb = scale_bits_from_amax(__ldg(ep.amax_b));
+      const float alpha = (ep.alpha ? __ldg(ep.alpha) : 1.f) * __uint_as_float(inv_pow2_bits(sa)) * __uint_as_float(inv_pow2_bits(sb));
+      int buf = 0;
+      uint32_t tphase[2] = {0, 0};
+      float out_max = 0.f;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+        float acc[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+        const int nch = (nkb + KCH - 1) / KCH;
+        for (int c = 0; c < nch; ++c) {
+          // add the finished chunk sum of TMEM buffer `buf` into the register accumulators (round-to-nearest fp32)
+          mbar_wait(&tfull[buf], tphase[buf]);
+          tcgen05_fence_after();
+          const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + chalf * CH) + ((uint32_t)(lg * 32) << 16);
+#pragma unroll
+          for (int cc = 0; cc < CH / 32; ++cc) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + (uint32_t)(cc * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[cc * 32 + j] = __fadd_rn(acc[cc * 32 + j], __uint_as_float(r[j]));
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&tempty[buf]);
+          tphase[buf] ^= 1;
+          buf ^= 1;
+        }
+        const int row = m0 + lg * 32 + lane;
+        if (row < Mo) {
+#pragma unroll
+          for (int c = 0; c < CH / 32; ++c) {
+            const int col0 = n0 + chalf * CH + c * 32;
+            if (col0 >= No) continue;
+            float* dst = C + (size_t)row * ldc + col0;
+            const int nv = min(32, No - col0);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = alpha * acc[c * 32 + j];
+            const bool full32 = (nv == 32);
+            if (ep.mode == EPI_FWD) {
+              float bv[32];
+              if (ep.bias && full32 && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                  bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) bv[j] = (ep.bias && j < nv) ? __ldg(ep.bias + col0 + j) : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float y = v[j] + bv[j];
+                if (ep.act == GCBF_ACT_RELU) y = fmaxf(y, 0.f);
+                else if (ep.act == GCBF_ACT_TANH) y = tanhf(y);
+                v[j] = y;
+              }
+            } else if (ep.mode == EPI_DGRAD && ep.relu_src) {
+              const float* ms = ep.relu_src + (size_t)row * ep.ld_relu + col0;
+              if (full32 && ((reinterpret_cast<uintptr_t>(ms) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 m4 = __ldg(reinterpret_cast<const float4*>(ms + j));
+                  v[j] = m4.x > 0.f ? v[j] : 0.f; v[j + 1] = m4.y > 0.f ? v[j + 1] : 0.f;
+                  v[j + 2] = m4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = m4.w > 0.f ? v[j + 3] : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) v[j] = (__ldg(ms + j) > 0.f) ? v[j] : 0.f;
+              }
+            }
+            if (ep.mode == EPI_WGRAD && ep.atomic) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) atomicAdd(dst + j, v[j]);
+            } else if (ep.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) { v[j] += dst[j]; dst[j] = v[j]; }
+            } else if (nv == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) dst[j] = v[j];
+            }
+            if (ep.amax_out) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) out_max = fmaxf(out_max, fabsf(v[j]));
+            }
+          }
+        }
+      }
+      if (ep.amax_out) {
+        const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(out_max));   // non-negative floats order like uints
+        if (lane == 0 && m) atomicMax(ep.amax_out, m);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, K::TMEM_COLS);
+  }
+}
+
+// ---- amax and the [hi | lo] split ------------------------------------------------------------------------------
+// max|x| over a strided [rows, cols] fp32 matrix -> atomicMax on the float bits (non-negative floats order like uints)
+__global__ void amax_kernel(const float* __restrict__ src, int ld, int rows, int cols, uint32_t* __restrict__ slot, int vec4) {
+  float m = 0.f;
+  if (vec4) {
+    const int w = cols >> 2;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+      const float4* p = reinterpret_cast<const float4*>(src + (size_t)r * ld);
+      for (int c = threadIdx.x; c < w; c += blockDim.x) {
+        const float4 x = __ldg(p + c);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+      }
+    }
+  } else {
+    for (int r = blockIdx.x; r < rows; r += gridDim.x)
+      for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, fabsf(__ldg(src + (size_t)r * ld + c)));
+  }
+  const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  __shared__ uint32_t part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0u;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if (threadIdx.x == 0 && v) atomicMax(slot, v);
+  }
+}
+
+// dst planes: hi at dst, lo at dst + rows*ld_h (halves); element (r, c) of the fp32 source -> same (r, c).  Each thread
+// converts 2 adjacent columns; a block walks `strip` rows so the optional column sums (bias gradient = colsum of dZ,
+// reference autograd of nn.Linear) need one atomic per column per block.
+constexpr int SPLIT_ROWS = 64;
+__global__ void split_h_kernel(const float* __restrict__ src, int ld, int rows, int cols, const uint32_t* __restrict__ amax,
+                               __half* __restrict__ dst, int ld_h, float* __restrict__ colsum) {
+  const float s = __uint_as_float(scale_bits_from_amax(__ldg(amax)));
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+  const int r0 = blockIdx.y * SPLIT_ROWS;
+  const size_t plane = (size_t)rows * ld_h;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < cols) {
+    const bool pair = (c + 1 < cols);
+    const int r1 = min(rows, r0 + SPLIT_ROWS);
+    for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      const float* p = src + (size_t)r * ld + c;
+      const float x0 = __ldg(p), x1 = pair ? __ldg(p + 1) : 0.f;
+      const float y0 = x0 * s, y1 = x1 * s;
+      const __half2 hi = __floats2half2_rn(y0, y1);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn(__fsub_rn(y0, hf.x), __fsub_rn(y1, hf.y));
+      __half* d = dst + (size_t)r * ld_h + c;
+      if (pair) {
+        *reinterpret_cast<__half2*>(d) = hi;
+        *reinterpret_cast<__half2*>(d + plane) = lo;
+      } else {
+        d[0] = __low2half(hi);
+        d[plane] = __low2half(lo);
+      }
+      s0 += x0; s1 += x1;
+    }
+  }
+  if (colsum) {
+    __shared__ float red[8][64];
+    red[threadIdx.y][2 * threadIdx.x] = s0;
+    red[threadIdx.y][2 * threadIdx.x + 1] = s1;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) { t0 += red[y][2 * threadIdx.x]; t1 += red[y][2 * threadIdx.x + 1]; }
+      if (c < cols) atomicAdd(colsum + c, t0);
+      if (c + 1 < cols) atomicAdd(colsum + c + 1, t1);
+    }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// one fp16 plane [rows][cols] (pitch ld_h halves).  K-major use: box {BK cols, tile_rows rows}, SWIZZLE_64B;
+// MN-major use: box {64 cols, BK rows}, SWIZZLE_128B.
+static int make_map(CUtensorMap* map, const __half* base, int rows, int cols, int ld_h, bool mn_major, int tile_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return GCBF_E_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_h * 2};
+  cuuint32_t box[2] = {(cuuint32_t)(mn_major ? MN_BOX : BK), (cuuint32_t)(mn_major ? BK : tile_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d mn=%d", (int)r, rows, cols, ld_h, (int)mn_major);
+    return GCBF_E_CUDA;
+  }
+  return GCBF_OK;
+}
+
+// companion operand as the GEMM sees it: plane [rows][cols]; K-major: rows = output index, cols = contraction;
+// MN-major: rows = contraction, cols = output index
+struct Operand {
+  const __half* hi; int rows; int cols; int ld_h; bool mn_major;
+  const __half* lo() const { return hi + (size_t)rows * ld_h; }
+};
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo, int No, int Kc, int splits, EpiParams ep,
+                  cudaStream_t st) {
+  using K = Cfg<BN>;
+  CUtensorMap mah, mal, mbh, mbl;
+  if (int rc = make_map(&mah, A.hi, A.rows, A.cols, A.ld_h, A_MN, BM)) return rc;
+  if (int rc = make_map(&mal, A.lo(), A.rows, A.cols, A.ld_h, A_MN, BM)) return rc;
+  if (int rc = make_map(&mbh, B.hi, B.rows, B.cols, B.ld_h, B_MN, BN)) return rc;
+  if (int rc = make_map(&mbl, B.lo(), B.rows, B.cols, B.ld_h, B_MN, BN)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCBF_CUDA_OK(cudaFuncSetAttribute(gemm_h_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles_m = ceil_div(Mo, BM), tiles_n = ceil_div(No, BN);
+  const int kblocks = ceil_div(Kc, BK);
+  const int kps = ceil_div(kblocks, splits);
+  const int nsplit = ceil_div(kblocks, kps);
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ctas = max(1, min(tiles_m * tiles_n, max(1, sms / nsplit)));
+  dim3 grid(ctas, nsplit);
+  gemm_h_kernel<BN, A_MN, B_MN><<<grid, NUM_THREADS, K::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, C, ldc, Mo, No, tiles_m, tiles_n, kps,
+                                                                        kblocks, ep);
+  GCBF_LAUNCH_OK();
+  return GCBF_OK;
+}
+
+static int check_plane(const void* p, int ld_h, const char* what) {
+  if (!p || (reinterpret_cast<uintptr_t>(p) & 15) || (ld_h & 7)) {
+    set_error("%s: fp16 companion must be 16-byte aligned with a pitch that is a multiple of 8 halves (ptr=%p ld=%d)", what, p, ld_h);
+    return GCBF_E_INVALID;
+  }
+  return GCBF_OK;
+}
+
+}  // namespace th
+}  // namespace gcbf
+
+using namespace gcbf;
+
+// ---- C ABI ------------------------------------------------------------------------------------------------------
+extern "C" int gcbf_amax_f32(const float* src, int ld, int rows, int cols, void* amax_slot, int accumulate, void* stream) {
+  GCBF_REQUIRE(amax_slot && rows >= 0 && cols >= 0 && ld >= cols, "gcbf_amax_f32: bad arguments rows=%d cols=%d ld=%d", rows, cols, ld);
+  cudaStream_t st = as_stream(stream);
+  if (!accumulate) GCBF_CUDA_OK(cudaMemsetAsync(amax_slot, 0, 4, st));
+  if (rows == 0 || cols == 0) return GCBF_OK;
+  GCBF_REQUIRE(src, "gcbf_amax_f32: null src");
+  const int vec4 = ((cols & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) ? 1 : 0;
+  const int work = vec4 ? cols / 4 : cols;
+  const int threads = work >= 256 ? 256 : (work >= 128 ? 128 : 64);
+  const int blocks = (int)imin64(rows, (int64_t)kNumSMs * (2048 / threads));
+  th::amax_kernel<<<blocks, threads, 0, st>>>(src, ld, rows, cols, reinterpret_cast<uint32_t*>(amax_slot), vec4);
+  GCBF_LAUNCH_OK();
+  return GCBF_OK;
+}
+
+extern "C" int gcbf_split_f16(const float* src, int ld, int rows, int cols, const void* amax_slot, void* dst, int ld_h,
+                              float* colsum, void* stream) {
+  GCBF_REQUIRE(amax_slot && dst && rows >= 0 && cols >= 0 && ld >= cols && ld_h >= cols, "gcbf_split_f16: bad arguments rows=%d cols=%d", rows, cols);
+  if (int rc = th::check_plane(dst, ld_h, "gcbf_split_f16")) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (colsum) GCBF_CUDA_OK(cudaMemsetAsync(colsum, 0, (size_t)cols * 4, st));
+  if (rows == 0 || cols == 0) return GCBF_OK;
+  GCBF_REQUIRE(src, "gcbf_split_f16: null src");
+  dim3 grid(ceil_div(cols, 64), ceil_div(rows, th::SPLIT_ROWS)), block(32, 8);
+  th::split_h_kernel<<<grid, block, 0, st>>>(src, ld, rows, cols, reinterpret_cast<const uint32_t*>(amax_slot),
+                                            reinterpret_cast<__half*>(dst), ld_h, colsum);
+  GCBF_LAUNCH_OK();
+  return GCBF_OK;
+}
+
+extern "C" int gcbf_linear_h_supported(int M, int N, int K) {
+  return (M >= 256 && N >= 96 && K >= 64 && (long long)M * N * K >= (1ll << 24)) ? 1 : 0;
+}
+
+// Y[M,N] = act(alpha * X W^T + bias): A = X companion [M][K] (K-major), B = W companion [N][K] (K-major)
+extern "C" int gcbf_linear_fwd_h(const void* Xh, int ldxh, const void* x_amax, const void* Wh, int ldwh, const void* w_amax,
+                                 const float* bias, const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act,
+                                 void* out_amax, void* stream) {
+  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && ldy >= N && Y && x_amax && w_amax, "gcbf_linear_fwd_h: bad arguments M=%d N=%d K=%d", M, N, K);
+  if (int rc = th::check_plane(Xh, ldxh, "gcbf_linear_fwd_h X")) return rc;
+  if (int rc = th::check_plane(Wh, ldwh, "gcbf_linear_fwd_h W")) return rc;
+  cudaStream_t st = as_stream(stream);
+  th::EpiParams ep{};
+  ep.mode = th::EPI_FWD; ep.alpha = inv_sigma; ep.bias = bias; ep.act = act;
+  ep.amax_a = reinterpret_cast<const uint32_t*>(x_amax); ep.amax_b = reinterpret_cast<const uint32_t*>(w_amax);
+  ep.amax_out = reinterpret_cast<uint32_t*>(out_amax);
+  if (out_amax) GCBF_CUDA_OK(cudaMemsetAsync(out_amax, 0, 4, st));
+  th::Operand A{reinterpret_cast<const __half*>(Xh), M, K, ldxh, false}, B{reinterpret_cast<const __half*>(Wh), N, K, ldwh, false};
+  return (N > 128) ? th::launch<256, false, false>(A, B, Y, ldy, M, N, K, 1, ep, st)
+                   : th::launch<128, false, false>(A, B, Y, ldy, M, N, K, 1, ep, st);
+}
+
+// dX[M,K] (+)= alpha * dZ W (* relu mask): A = dZ companion [M][N] (K-major: contraction over N), B = W companion [N][K] (MN-major)
+extern "C" int gcbf_linear_bwd_data_h(const void* dZh, int lddzh, const void* dz_amax, const void* Wh, int ldwh,
+                                      const void* w_amax, const float* inv_sigma, const float* relu_src, int ld_relu, float* dX,
+                                      int lddx, int M, int N, int K, int accumulate, void* out_amax, void* stream) {
+  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && lddx >= K && dX && dz_amax && w_amax, "gcbf_linear_bwd_data_h: bad arguments M=%d N=%d K=%d", M, N, K);
+  GCBF_REQUIRE(!relu_src || ld_relu >= K, "gcbf_linear_bwd_data_h: ld_relu");
+  if (int rc = th::check_plane(dZh, lddzh, "gcbf_linear_bwd_data_h dZ")) return rc;
+  if (int rc = th::check_plane(Wh, ldwh, "gcbf_linear_bwd_data_h W")) return rc;
+  cudaStream_t st = as_stream(stream);
+  th::EpiParams ep{};
+  ep.mode = th::EPI_DGRAD; ep.alpha = inv_sigma; ep.relu_src = relu_src; ep.ld_relu = ld_relu; ep.accumulate = accumulate;
+  ep.amax_a = reinterpret_cast<const uint32_t*>(dz_amax); ep.amax_b = reinterpret_cast<const uint32_t*>(w_amax);
+  ep.amax_out = reinterpret_cast<uint32_t*>(out_amax);
+  if (out_amax) GCBF_CUDA_OK(cudaMemsetAsync(out_amax, 0, 4, st));
+  th::Operand A{reinterpret_cast<const __half*>(dZh), M, N, lddzh, false}, B{reinterpret_cast<const __half*>(Wh), N, K, ldwh, true};
+  return (K > 128) ? th::launch<256, false, true>(A, B, dX, lddx, M, K, N, 1, ep, st)
+                   : th::launch<128, false, true>(A, B, dX, lddx, M, K, N, 1, ep, st);
+}
+
+// dW[N,K] (+)= alpha * dZ^T X: A = dZ companion [M][N] (MN-major), B = X companion [M][K] (MN-major); contraction over M
+extern "C" int gcbf_linear_bwd_weight_h(const void* dZh, int lddzh, const void* dz_amax, const void* Xh, int ldxh,
+                                        const void* x_amax, const float* inv_sigma, float* dW, int lddw, int M, int N, int K,
+                                        int accumulate, void* stream) {
+  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && lddw >= K && dW && dz_amax && x_amax, "gcbf_linear_bwd_weight_h: bad arguments M=%d N=%d K=%d", M, N, K);
+  if (int rc = th::check_plane(dZh, lddzh, "gcbf_linear_bwd_weight_h dZ")) return rc;
+  if (int rc = th::check_plane(Xh, ldxh, "gcbf_linear_bwd_weight_h X")) return rc;
+  cudaStream_t st = as_stream(stream);
+  th::EpiParams ep{};
+  ep.mode = th::EPI_WGRAD; ep.alpha = inv_sigma; ep.accumulate = accumulate;
+  ep.amax_a = reinterpret_cast<const uint32_t*>(dz_amax); ep.amax_b = reinterpret_cast<const uint32_t*>(x_amax);
+  const int BN = (K > 128) ? 256 : 128;
+  const int tiles = ceil_div(N, th::BM) * ceil_div(K, BN);
+  int splits = 1;
+  if (tiles < kNumSMs) splits = max(1, min(ceil_div(M, 256), kNumSMs / tiles));
+  ep.atomic = splits > 1;
+  if (ep.atomic && !accumulate) GCBF_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)K * 4, N, st));
+  th::Operand A{reinterpret_cast<const __half*>(dZh), M, N, lddzh, true}, B{reinterpret_cast<const __half*>(Xh), M, K, ldxh, true};
+  return (BN == 256) ? th::launch<256, true, true>(A, B, dW, lddw, N, K, M, splits, ep, st)
+                     : th::launch<128, true, true>(A, B, dW, lddw, N, K, M, splits, ep, st);
+}

@@ -1,5 +1,5 @@
-// C-ABI dispatch of the linear layers (K3): picks the tcgen05 3xTF32 kernel when the shape qualifies,
-// otherwise the exact-fp32 SIMT kernel.  Reference op site: gcbf/nn/mlp.py:44-47 (nn.Linear + ReLU chain).
+// C-ABI dispatch of the fp32 linear layers (K3): skinny-K stream kernels for in-features <= 16, otherwise the exact-fp32
+// SIMT tile kernel.  (Big layers run on the tensor cores through gcbf_linear_*_h, gemm_tcgen05_f16.cu.)  Reference op site: gcbf/nn/mlp.py:44-47 (nn.Linear + ReLU chain).
 #include "common.cuh"
 
 namespace gcbf {
@@ -17,17 +17,6 @@ int launch_skinny_dgrad(const float* dZ, int lddz, const float* W, int ldw, cons
                         int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
 int launch_skinny_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw,
                         float* db, int M, int N, int K, int accumulate, cudaStream_t st);
-#ifdef GCBF_WITH_TCGEN05
-bool tc_fwd_supported(int ldx, int ldw, int ldy, int M, int N, int K, bool forced);
-int launch_tc_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
-                  int ldy, int M, int N, int K, int act, cudaStream_t st);
-bool tc_dgrad_supported(int lddz, int ldw, int lddx, int M, int N, int K, bool forced);
-int launch_tc_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src,
-                    int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
-bool tc_wgrad_supported(int lddz, int ldx, int lddw, int M, int N, int K, bool forced);
-int launch_tc_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw,
-                    float* db, int M, int N, int K, int accumulate, cudaStream_t st);
-#endif
 }  // namespace gcbf
 
 using namespace gcbf;
@@ -51,10 +40,6 @@ extern "C" int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw,
   if (M == 0) return GCBF_OK;
   GCBF_REQUIRE(X && W && Y, "gcbf_linear_fwd: null pointer");
   cudaStream_t st = as_stream(stream);
-#ifdef GCBF_WITH_TCGEN05
-  if (impl != 1 && tc_fwd_supported(ldx, ldw, ldy, M, N, K, impl == 2)) { g_last_impl = 2;
-    return launch_tc_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st); }
-#endif
   if (impl == 2) { set_error("gcbf_linear_fwd: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
   if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {   // K <= 16: HBM-bound stream, not a GEMM tile
     g_last_impl = 3;
@@ -72,10 +57,6 @@ extern "C" int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, i
   if (M == 0) return GCBF_OK;
   GCBF_REQUIRE(dZ && W && dX, "gcbf_linear_bwd_data: null pointer");
   cudaStream_t st = as_stream(stream);
-#ifdef GCBF_WITH_TCGEN05
-  if (impl != 1 && tc_dgrad_supported(lddz, ldw, lddx, M, N, K, impl == 2)) { g_last_impl = 2;
-    return launch_tc_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st); }
-#endif
   if (impl == 2) { set_error("gcbf_linear_bwd_data: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
   if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {
     g_last_impl = 3;
@@ -99,10 +80,6 @@ extern "C" int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X,
     return GCBF_OK;
   }
   GCBF_REQUIRE(dZ && X, "gcbf_linear_bwd_weight: null pointer");
-#ifdef GCBF_WITH_TCGEN05
-  if (impl != 1 && tc_wgrad_supported(lddz, ldx, lddw, M, N, K, impl == 2)) { g_last_impl = 2;
-    return launch_tc_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st); }
-#endif
   if (impl == 2) { set_error("gcbf_linear_bwd_weight: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
   if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {
     g_last_impl = 3;

@@ -35,8 +35,12 @@ _SIGS = {
     'gcbf_linear_fwd': (c_int, [P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_linear_bwd_data': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_linear_bwd_weight': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
-    'gcbf_set_gemm_workspace': (c_int, [P, c_size_t]),
-    'gcbf_gemm_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'gcbf_amax_f32': (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
+    'gcbf_split_f16': (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
+    'gcbf_linear_h_supported': (c_int, [c_int, c_int, c_int]),
+    'gcbf_linear_fwd_h': (c_int, [P, c_int, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    'gcbf_linear_bwd_data_h': (c_int, [P, c_int, P, P, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    'gcbf_linear_bwd_weight_h': (c_int, [P, c_int, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_act_bwd': (c_int, [P, P, P, c_int64, c_int, P]),
     'gcbf_attn_aggr_fwd': (c_int, [P, c_int, P, P, c_int, c_int, P, P, c_int, P]),
     'gcbf_attn_aggr_bwd': (c_int, [P, c_int, P, P, c_int, c_int, P, c_int, P, c_int, P, c_int, P]),
@@ -97,7 +101,8 @@ def check(rc, what):
 
 
 # kernels launched by one call of each entry point (for bench.py's `gpu_launches`; memsets are not counted)
-_KERNELS_PER_CALL = {'gcbf_radius_graph_count': 2, 'gcbf_sn_power_iter': 4, 'gcbf_sn_grad_fixup': 2, 'gcbf_linear_bwd_weight': 2}
+_KERNELS_PER_CALL = {'gcbf_radius_graph_count': 2, 'gcbf_sn_power_iter': 4, 'gcbf_sn_grad_fixup': 2, 'gcbf_linear_bwd_weight': 2,
+                     'gcbf_linear_h_supported': 0}
 KERNEL_LAUNCHES = 0
 ABI_CALLS = 0
 

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from .. import _C
+from .. import _C, ops
 from ..controller import GNNController
 from ..data import Batch, Data, agent_row_index
 from ..nn import MLP, CBFGNNLayer, GraphSequential
@@ -198,6 +198,7 @@ class GCBF(Algorithm):
         b = self._ensure_bucket()
         b.step += 1
         b.sumsq.zero_()
+        ops.WEIGHT_EPOCH += 1                 # the kernel below rewrites the parameters: fp16 weight companions are stale
         for i, lr in enumerate((self.lr_cbf, self.lr_actor)):
             lo, hi = b.ranges[i]
             g = b.grad[lo:hi]

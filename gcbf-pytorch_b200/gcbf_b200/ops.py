@@ -26,26 +26,37 @@ GEMM_IMPL = 0   # 0 auto, 1 force fp32 SIMT, 2 force tcgen05 (tests flip this)
 
 class _GemmTimer:
     """Optional CUDA-event timing of every linear-layer launch (bench.py's roofline numbers).  Events are recorded
-    on the launching stream around each C-ABI GEMM call; summary() synchronises and adds them up."""
+    on the launching stream around each C-ABI GEMM call; summary() synchronises and adds them up.  Operand preparation
+    of the tensor-core path (amax + fp16 [hi|lo] split, shared by the GEMMs a matrix takes part in) is timed separately."""
 
     def __init__(self):
         self.on = False
         self.records = []
+        self.prep = []
 
     def enable(self):
-        self.on, self.records = True, []
+        self.on, self.records, self.prep = True, [], []
 
     def disable(self):
-        self.on, self.records = False, []
+        self.on, self.records, self.prep = False, [], []
 
-    def run(self, flops, fn):
+    def run(self, flops, fn, impl=None):
         if not self.on:
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
-        self.records.append((e0, e1, flops, _C.lib().gcbf_last_gemm_impl()))
+        self.records.append((e0, e1, flops, impl if impl is not None else _C.lib().gcbf_last_gemm_impl()))
+
+    def run_prep(self, fn):
+        if not self.on:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.prep.append((e0, e1))
 
     def summary(self):
         torch.cuda.synchronize()
@@ -55,9 +66,11 @@ class _GemmTimer:
             b[0] += e0.elapsed_time(e1)
             b[1] += flops
             b[2] += 1
+        prep_ms = sum(e0.elapsed_time(e1) for e0, e1 in self.prep)
         tensor = by[2][1] > by[1][1]
         ms, flops, n = by[2] if tensor else by[1]
-        return dict(kernel='gemm_tcgen05_3xtf32' if tensor else 'gemm_simt_kernel', ms=ms, flops=flops, launches=n, tensor=tensor,
+        return dict(kernel='gemm_tcgen05_3xfp16' if tensor else 'gemm_simt_kernel', ms=ms, flops=flops, launches=n, tensor=tensor,
+                    prep_ms=prep_ms, prep_launches=len(self.prep),
                     other_ms=(by[1] if tensor else by[2])[0], other_flops=(by[1] if tensor else by[2])[1])
 
 
@@ -79,29 +92,107 @@ def _mat(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
 # ----------------------------------------------------------------------------------------------------
 # raw ops (each = one C-ABI entry point)
 # ----------------------------------------------------------------------------------------------------
-_GEMM_WS = {'buf': None, 'bytes': 0}
 USE_TCGEN05 = True     # set False to keep every layer on the fp32 SIMT kernel
+WEIGHT_EPOCH = 0       # bumped whenever a raw kernel rewrites parameters (GCBF.optim_step): invalidates weight companions
 
 
-def _ensure_gemm_ws(M, N, K, device):
-    """The C library never allocates: register a scratch buffer big enough for this layer's tcgen05 operands."""
-    if not USE_TCGEN05 or GEMM_IMPL == 1 or (M < 256 and GEMM_IMPL != 2):
-        return
-    lib = _C.lib()
-    if not lib.gcbf_has_tcgen05():
-        return
-    need = int(lib.gcbf_gemm_workspace_bytes(M, N, K))
-    if need > _GEMM_WS['bytes']:
-        size = int(need * 1.1) + (1 << 20)
-        _GEMM_WS['buf'] = torch.empty(size, device=device, dtype=torch.uint8)
-        _GEMM_WS['bytes'] = size
-        lib.gcbf_set_gemm_workspace(_GEMM_WS['buf'].data_ptr(), size)
+@dataclass
+class H16:
+    """fp16 [hi | lo] companion of an fp32 matrix (same row-major layout, pitch `ld` halves): x * s = hi + lo with the
+    per-tensor power-of-two scale s derived from `amax` (device int32 = float bits of max|x|).  One companion serves
+    every GEMM the matrix takes part in (K-major or MN-major operand, csrc/gemm_tcgen05_f16.cu)."""
+    buf: torch.Tensor
+    amax: torch.Tensor
+    rows: int
+    cols: int
+    ld: int
 
 
-def release_gemm_workspace():
-    if _GEMM_WS['buf'] is not None:
-        _C.lib().gcbf_set_gemm_workspace(None, 0)
-    _GEMM_WS['buf'], _GEMM_WS['bytes'] = None, 0
+def use_h(M: int, N: int, K: int) -> bool:
+    """Does the [M,K] x [N,K] layer (forward, data-grad and weight-grad alike) run on the tcgen05 3xFP16 kernel?"""
+    if not USE_TCGEN05 or GEMM_IMPL == 1:
+        return False
+    if GEMM_IMPL == 2:
+        return True
+    return M >= 256 and N >= 96 and K >= 96 and M * N * K >= (1 << 24)
+
+
+def amax_slot(device) -> torch.Tensor:
+    return _empty(1, device=device, dtype=torch.int32)
+
+
+def split_h(t: torch.Tensor, amax: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
+            persistent: bool = False, into: Optional[H16] = None) -> H16:
+    """amax (unless the producer already supplied it) + fp16 [hi|lo] split; `colsum` (fp32 [cols]) optionally receives
+    the column sums of t (the bias gradient when t = dZ)."""
+    m, ld = _mat(t)
+    rows, cols = m.shape
+    ld_h = (cols + 7) // 8 * 8
+    if into is not None and into.rows == rows and into.cols == cols:
+        buf, own_amax = into.buf, into.amax
+    else:
+        alloc = torch.empty if persistent else _empty
+        buf = alloc(2, rows, ld_h, device=m.device, dtype=torch.float16)
+        own_amax = alloc(1, device=m.device, dtype=torch.int32)
+
+    def go():
+        nonlocal amax
+        if amax is None:
+            amax = own_amax
+            call('gcbf_amax_f32', ptr(m), ld, rows, cols, ptr(amax), 0)
+        call('gcbf_split_f16', ptr(m), ld, rows, cols, ptr(amax), ptr(buf), ld_h, ptr(colsum))
+    GEMM_TIMER.run_prep(go)
+    return H16(buf, amax, rows, cols, ld_h)
+
+
+def weight_h(W: torch.Tensor) -> H16:
+    """Companion of a weight matrix, re-made only when the weights changed (optimizer step / in-place update).  The
+    cache entry lives on the tensor object itself, so it can never outlive the weights it was made from."""
+    stamp = (WEIGHT_EPOCH, W._version, W.data_ptr(), tuple(W.shape))
+    ent = getattr(W, '_gcbf_h16', None)
+    if ent is not None and ent[0] == stamp:
+        return ent[1]
+    h = split_h(W.detach(), persistent=True, into=ent[1] if ent is not None else None)
+    W._gcbf_h16 = (stamp, h)
+    return h
+
+
+def linear_fwd_h(xh: H16, wh: H16, b, inv_sigma, act, out=None, out_amax=None):
+    M, K, N = xh.rows, xh.cols, wh.rows
+    assert wh.cols == K, (M, K, wh.rows, wh.cols)
+    if out is None:
+        out = _empty(M, N, device=xh.buf.device, dtype=torch.float32)
+    y, ldy = _mat(out)
+    assert y.data_ptr() == out.data_ptr()
+    GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_fwd_h', ptr(xh.buf), xh.ld, ptr(xh.amax), ptr(wh.buf), wh.ld,
+                                                 ptr(wh.amax), ptr(b), ptr(inv_sigma), ptr(y), ldy, M, N, K, act, ptr(out_amax)), impl=2)
+    return out
+
+
+def linear_bwd_data_h(dzh: H16, wh: H16, inv_sigma, relu_src, out=None, accumulate=False, out_amax=None):
+    M, N, K = dzh.rows, dzh.cols, wh.cols
+    assert wh.rows == N
+    if out is None:
+        assert not accumulate
+        out = _empty(M, K, device=dzh.buf.device, dtype=torch.float32)
+    o, ldo = _mat(out)
+    assert o.data_ptr() == out.data_ptr()
+    rs, ldr = (None, 0)
+    if relu_src is not None:
+        rs, ldr = _mat(relu_src)
+    GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_data_h', ptr(dzh.buf), dzh.ld, ptr(dzh.amax), ptr(wh.buf), wh.ld,
+                                                 ptr(wh.amax), ptr(inv_sigma), ptr(rs), ldr, ptr(o), ldo, M, N, K,
+                                                 1 if accumulate else 0, ptr(out_amax)), impl=2)
+    return out
+
+
+def linear_bwd_weight_h(dzh: H16, xh: H16, inv_sigma):
+    M, N, K = dzh.rows, dzh.cols, xh.cols
+    assert xh.rows == M
+    dW = _empty(N, K, device=dzh.buf.device, dtype=torch.float32)
+    GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_weight_h', ptr(dzh.buf), dzh.ld, ptr(dzh.amax), ptr(xh.buf), xh.ld,
+                                                 ptr(xh.amax), ptr(inv_sigma), ptr(dW), K, M, N, K, 0), impl=2)
+    return dW
 
 
 def linear_fwd(x, W, b, inv_sigma, act, out=None):
@@ -110,11 +201,12 @@ def linear_fwd(x, W, b, inv_sigma, act, out=None):
     M, K = x.shape
     N = W.shape[0]
     assert W.shape[1] == K, (x.shape, W.shape)
+    if use_h(M, N, K):
+        return linear_fwd_h(split_h(x), weight_h(W), b, inv_sigma, act, out=out)
     if out is None:
         out = _empty(M, N, device=x.device, dtype=torch.float32)
     y, ldy = _mat(out)
     assert y.data_ptr() == out.data_ptr()
-    _ensure_gemm_ws(M, N, K, x.device)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_fwd', ptr(x), ldx, ptr(W), ldw, ptr(b), ptr(inv_sigma), ptr(y), ldy,
                                                  M, N, K, act, GEMM_IMPL))
     return out
@@ -126,6 +218,8 @@ def linear_bwd_data(dz, W, inv_sigma, relu_src, out=None, accumulate=False):
     M, N = dz.shape
     K = W.shape[1]
     assert W.shape[0] == N
+    if use_h(M, N, K):
+        return linear_bwd_data_h(split_h(dz), weight_h(W), inv_sigma, relu_src, out=out, accumulate=accumulate)
     if out is None:
         assert not accumulate
         out = _empty(M, K, device=dz.device, dtype=torch.float32)
@@ -134,7 +228,6 @@ def linear_bwd_data(dz, W, inv_sigma, relu_src, out=None, accumulate=False):
     rs, ldr = (None, 0)
     if relu_src is not None:
         rs, ldr = _mat(relu_src)
-    _ensure_gemm_ws(M, N, K, dz.device)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_data', ptr(dz), lddz, ptr(W), ldw, ptr(inv_sigma), ptr(rs), ldr,
                                                  ptr(o), ldo, M, N, K, 1 if accumulate else 0, GEMM_IMPL))
     return out
@@ -145,9 +238,11 @@ def linear_bwd_weight(dz, x, inv_sigma, need_bias=True):
     x, ldx = _mat(x)
     M, N = dz.shape
     K = x.shape[1]
+    if use_h(M, N, K):
+        db = _empty(N, device=dz.device, dtype=torch.float32) if need_bias else None
+        return linear_bwd_weight_h(split_h(dz, colsum=db), split_h(x), inv_sigma), db
     dW = _empty(N, K, device=dz.device, dtype=torch.float32)
     db = _empty(N, device=dz.device, dtype=torch.float32) if need_bias else None
-    _ensure_gemm_ws(M, N, K, dz.device)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_weight', ptr(dz), lddz, ptr(x), ldx, ptr(inv_sigma), ptr(dW), K,
                                                  ptr(db), M, N, K, 0, GEMM_IMPL))
     return dW, db
@@ -302,21 +397,34 @@ class MLPCtx:
     acts: List[torch.Tensor] = field(default_factory=list)      # acts[0] = input, acts[l] = output of layer l
     inv_sigma: List[Optional[torch.Tensor]] = field(default_factory=list)
     uv: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = field(default_factory=list)
+    acts_h: List[Optional[H16]] = field(default_factory=list)  # acts_h[l] = fp16 companion of acts[l] when layer l is on tcgen05
 
 
 def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool) -> Tuple[torch.Tensor, Optional[MLPCtx]]:
     ctx = MLPCtx() if save else None
     if save:
         ctx.acts.append(x)
-    for L in layers:
+    x_amax = None                         # amax of x when the producing GEMM's epilogue already reduced it
+    for l, L in enumerate(layers):
         inv_sigma = None
         if L.sn:
             # old-style torch spectral_norm in training mode: one power iteration per forward, even under
             # no_grad (the reference never calls .eval())
             inv_sigma = sn_power_iter(L.W, L.u, L.v)
-        x = linear_fwd(x, L.W, L.b, inv_sigma, L.act)
+        M, K = x.shape
+        N = L.W.shape[0]
+        xh = None
+        if use_h(M, N, K):
+            xh = split_h(x, amax=x_amax)
+            nxt = layers[l + 1] if l + 1 < len(layers) else None
+            x_amax = amax_slot(x.device) if (nxt is not None and use_h(M, nxt.W.shape[0], N)) else None
+            x = linear_fwd_h(xh, weight_h(L.W), L.b, inv_sigma, L.act, out_amax=x_amax)
+        else:
+            x = linear_fwd(x, L.W, L.b, inv_sigma, L.act)
+            x_amax = None
         if save:
             ctx.acts.append(x)
+            ctx.acts_h.append(xh)
             ctx.inv_sigma.append(inv_sigma)
             ctx.uv.append((L.u.clone(), L.v.clone()) if L.sn else None)
     return x, ctx
@@ -335,10 +443,39 @@ def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, ne
         dz = act_bwd(dz, ctx.acts[last + 1], ACT_TANH)
     elif layers[last].act == ACT_RELU:
         dz = act_bwd(dz, ctx.acts[last + 1], ACT_RELU)
+    dz_amax = None                        # amax of dz when the producing data-grad epilogue already reduced it
     for l in range(last, -1, -1):
         L = layers[l]
         x_in = ctx.acts[l]
         inv_sigma = ctx.inv_sigma[l]
+        M, N = dz.shape
+        K = x_in.shape[1]
+        if use_h(M, N, K):
+            # one fp16 companion of dz serves the weight-grad (MN-major A) and the data-grad (K-major A); the bias
+            # gradient (column sums of dz) is fused into the split
+            db = None if SKIP_WGRAD else _empty(N, device=dz.device, dtype=torch.float32)
+            dzh = split_h(dz, amax=dz_amax, colsum=db)
+            if SKIP_WGRAD:
+                grads[l] = (None, None)
+            else:
+                xh = ctx.acts_h[l] if ctx.acts_h[l] is not None else split_h(x_in)
+                dW = linear_bwd_weight_h(dzh, xh, inv_sigma)
+                if L.sn:
+                    u, v = ctx.uv[l]
+                    sn_grad_fixup(dW, L.W, u, v, inv_sigma)
+                grads[l] = (dW, db)
+            wh = weight_h(L.W)
+            if l > 0:
+                assert layers[l - 1].act == ACT_RELU
+                Kp = ctx.acts[l - 1].shape[1]
+                dz_amax = amax_slot(dz.device) if use_h(M, K, Kp) else None
+                dz = linear_bwd_data_h(dzh, wh, inv_sigma, x_in, out_amax=dz_amax)
+            elif need_dx:
+                dz = linear_bwd_data_h(dzh, wh, inv_sigma, None, out=dx_out, accumulate=dx_accumulate)
+            else:
+                dz = None
+            continue
+        dz_amax = None
         if SKIP_WGRAD:
             grads[l] = (None, None)
         else:

@@ -41,10 +41,10 @@ extern "C" {
 
 const char* gcbf_last_error(void);
 int gcbf_abi_version(void);
-/* 1 if the library was built with the tcgen05 (3xTF32) GEMM path compiled in, else 0 */
+/* 1 if the library was built with the tcgen05 (3xFP16) GEMM path compiled in, else 0 */
 int gcbf_has_tcgen05(void);
-/* which kernel the most recent gcbf_linear_* call on this thread launched: 1 = fp32 SIMT tile GEMM, 2 = tcgen05 3xTF32,
- * 3 = fp32 skinny-K stream kernel (in-features <= 16) */
+/* which kernel the most recent gcbf_linear_* call on this thread launched: 1 = fp32 SIMT tile GEMM,
+ * 3 = fp32 skinny-K stream kernel (in-features <= 16).  (The tcgen05 path has its own entry points, gcbf_linear_*_h.) */
 int gcbf_last_gemm_impl(void);
 
 /* ---------------------------------------------------------------------------------------------------
@@ -92,7 +92,7 @@ int gcbf_edge_input_fwd(const float* x, int node_dim, const float* edge_attr, in
  *   bwd_data  : dX[M,K] (+)= inv_sigma * dZ[M,N] W[N,K]   (* (relu_src[M,K] > 0) if relu_src != NULL)
  *   bwd_weight: dW[N,K] (+)= inv_sigma * dZ[M,N]^T X[M,K] ; db[N] (+)= colsum(dZ)   (db may be NULL)
  *               accumulate != 0 adds into dW/db, otherwise they are overwritten.
- * impl: 0 = auto, 1 = fp32 SIMT kernel, 2 = tcgen05 3xTF32 kernel (error if shape unsupported).
+ * impl: 0 = auto (skinny-K stream kernel when in-features <= 16, else the SIMT tile kernel), 1 = fp32 SIMT kernel.
  * ------------------------------------------------------------------------------------------------- */
 int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias,
                     const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act, int impl,
@@ -103,11 +103,35 @@ int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, int ldw, con
 int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma,
                            float* dW, int lddw, float* db, int M, int N, int K, int accumulate, int impl,
                            void* stream);
-/* Scratch for the tcgen05 path ([hi; lo] operand copies).  The library never allocates: the caller registers a
- * device buffer (process-wide; NULL unregisters, which routes every layer to the fp32 SIMT kernel) of at least
- * gcbf_gemm_workspace_bytes(M, N, K) bytes for the largest layer it will run. */
-int gcbf_set_gemm_workspace(void* device_ptr, size_t bytes);
-size_t gcbf_gemm_workspace_bytes(int M, int N, int K);
+/* ---------------------------------------------------------------------------------------------------
+ * K3 on the tensor cores (tcgen05 + TMEM + TMA, csrc/gemm_tcgen05_f16.cu): the same three products with
+ * error-compensated 3xFP16 arithmetic (fp32-grade: 22 significand bits per operand, fp32 accumulation).
+ * Operands are "companions": for an fp32 matrix X[rows, cols] the caller provides a device buffer of
+ * 2*rows*ld_h halves (ld_h a multiple of 8, 16-byte aligned) that gcbf_split_f16 fills with the planes
+ * hi = fp16(X*s), lo = fp16(X*s - hi) in X's own row-major layout; s is the power of two that puts
+ * max|X| (device uint32 slot holding its float bits, from gcbf_amax_f32 or a producer's out_amax) into
+ * [2^14, 2^15).  One companion serves every product the matrix is in (the tensor core reads it K-major
+ * or MN-major), so nothing is transposed or padded:
+ *   fwd_h       : Y  = act(inv_sigma * X W^T + bias)        X[M,K], W[N,K] companions
+ *   bwd_data_h  : dX (+)= inv_sigma * dZ W (* relu mask)    dZ[M,N], W[N,K] companions
+ *   bwd_weight_h: dW (+)= inv_sigma * dZ^T X                dZ[M,N], X[M,K] companions
+ * out_amax (optional, may be NULL): the epilogue atomically maxes |output| into it (zeroed first), which
+ * saves the amax pass when the output feeds the next layer's split.  gcbf_split_f16's `colsum`
+ * (optional) receives the column sums of the source = the bias gradient when the source is dZ.
+ * ------------------------------------------------------------------------------------------------- */
+int gcbf_amax_f32(const float* src, int ld, int rows, int cols, void* amax_slot, int accumulate, void* stream);
+int gcbf_split_f16(const float* src, int ld, int rows, int cols, const void* amax_slot, void* dst, int ld_h,
+                   float* colsum, void* stream);
+int gcbf_linear_h_supported(int M, int N, int K);
+int gcbf_linear_fwd_h(const void* Xh, int ldxh, const void* x_amax, const void* Wh, int ldwh, const void* w_amax,
+                      const float* bias, const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act,
+                      void* out_amax, void* stream);
+int gcbf_linear_bwd_data_h(const void* dZh, int lddzh, const void* dz_amax, const void* Wh, int ldwh,
+                           const void* w_amax, const float* inv_sigma, const float* relu_src, int ld_relu,
+                           float* dX, int lddx, int M, int N, int K, int accumulate, void* out_amax, void* stream);
+int gcbf_linear_bwd_weight_h(const void* dZh, int lddzh, const void* dz_amax, const void* Xh, int ldxh,
+                             const void* x_amax, const float* inv_sigma, float* dW, int lddw, int M, int N, int K,
+                             int accumulate, void* stream);
 /* dZ = dY * act'(Y) for the output activation (tanh: 1 - Y^2; relu: Y > 0).  In place allowed. */
 int gcbf_act_bwd(const float* dY, const float* Y, float* dZ, int64_t count, int act, void* stream);
 

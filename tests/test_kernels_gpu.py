@@ -136,15 +136,15 @@ def test_linear_bwd(M, N, K):
     assert (db.cpu().double() - dz.double().sum(0)).abs().max() < 3e-5 * max(1.0, dz.double().sum(0).abs().max().item())
 
 
-TC_SHAPES = [(256, 256, 64), (384, 128, 96), (1000, 2048, 2048), (2500, 256, 2048), (777, 2048, 260), (4096, 512, 1024),
+TC_SHAPES = [(256, 256, 96), (384, 128, 96), (1000, 2048, 2048), (2500, 256, 2048), (777, 2048, 260), (4096, 512, 1024),
              (300, 130, 100), (70000, 128, 256)]
 
 
 @pytest.mark.parametrize('M,N,K', TC_SHAPES)
-def test_linear_tcgen05_3xtf32(M, N, K):
+def test_linear_tcgen05_3xfp16(M, N, K):
     """tcgen05 path (forced) against fp64: forward with fused bias+ReLU, data grad with ReLU mask and accumulate, weight
-    grad + bias grad.  Tolerance 5e-5 of the output scale: 3xTF32 operands are fp32-exact, the residual is the tensor
-    core's truncating fp32 accumulation (~K/8 * 2^-24, measured by tools/acc_probe.py)."""
+    grad + bias grad (fused into the split of dZ).  Tolerance 1e-5 of the output scale: the [hi|lo] fp16 companions carry
+    22 significand bits and K is accumulated in 256-wide chunks promoted to fp32 registers (measured 1-2e-6)."""
     if not _C.lib().gcbf_has_tcgen05():
         pytest.skip('library built without the tcgen05 path')
     g = _g(M + N + K)
@@ -155,8 +155,8 @@ def test_linear_tcgen05_3xtf32(M, N, K):
     old = ops.GEMM_IMPL
     ops.GEMM_IMPL = 2
     try:
+        assert ops.use_h(M, N, K)
         y = ops.linear_fwd(xd, Wd, bd, alpha, ops.ACT_RELU)
-        assert _C.lib().gcbf_last_gemm_impl() == 2
         dx = ops.linear_bwd_data(dzd, Wd, alpha, rsd)
         dx_acc = torch.ones(M, K, device=DEV)
         ops.linear_bwd_data(dzd, Wd, None, None, out=dx_acc, accumulate=True)
@@ -165,10 +165,10 @@ def test_linear_tcgen05_3xtf32(M, N, K):
         ops.GEMM_IMPL = old
     x64, W64, dz64 = xd.double(), Wd.double(), dzd.double()
     e = lambda a, r: ((a.double() - r).abs().max() / r.abs().max()).item()
-    assert e(y, torch.relu(1.3 * (x64 @ W64.t()) + bd.double())) < 5e-5
-    assert e(dx, 1.3 * (dz64 @ W64) * (rsd > 0)) < 5e-5
-    assert e(dx_acc, dz64 @ W64 + 1) < 5e-5
-    assert e(dW, 1.3 * (dz64.t() @ x64)) < 5e-5
+    assert e(y, torch.relu(1.3 * (x64 @ W64.t()) + bd.double())) < 1e-5
+    assert e(dx, 1.3 * (dz64 @ W64) * (rsd > 0)) < 1e-5
+    assert e(dx_acc, dz64 @ W64 + 1) < 1e-5
+    assert e(dW, 1.3 * (dz64.t() @ x64)) < 1e-5
     assert e(db, dz64.sum(0)) < 1e-5
 
 
