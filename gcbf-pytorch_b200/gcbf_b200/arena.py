@@ -13,6 +13,7 @@ import torch
 
 _ALIGN = 256
 _CHUNK_BYTES = 1 << 30
+_ITEMSIZE = {}
 
 
 class StepArena:
@@ -23,10 +24,11 @@ class StepArena:
         self.off = 0
         self.active = False
         self.high_water = 0
+        self._views = {}
 
     def begin(self, device):
         if self.device != device:
-            self.chunks, self.device = [], device
+            self.chunks, self.device, self._views = [], device, {}
         self.cur, self.off, self.active = 0, 0, True
 
     def end(self):
@@ -34,26 +36,42 @@ class StepArena:
         used = sum(c.numel() for c in self.chunks[:self.cur]) + self.off
         self.high_water = max(self.high_water, used)
 
-    def _raw(self, nbytes: int) -> torch.Tensor:
+    def _typed(self, ci: int, dtype) -> torch.Tensor:
+        """dtype view of chunk `ci` (cached: one view per chunk and dtype)."""
+        key = (ci, dtype)
+        v = self._views.get(key)
+        if v is None:
+            v = self._views[key] = self.chunks[ci].view(dtype)
+        return v
+
+    def alloc(self, shape, dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        if n == 0:
+            return torch.empty(shape, device=self.device, dtype=dtype)
+        itemsize = _ITEMSIZE.get(dtype)
+        if itemsize is None:
+            itemsize = _ITEMSIZE[dtype] = torch.empty(0, dtype=dtype).element_size()
+        nbytes = n * itemsize
         need = (nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
         while True:
             if self.cur >= len(self.chunks):
-                size = max(_CHUNK_BYTES, int(need * 1.25))
+                size = max(_CHUNK_BYTES, int(need * 1.25) // _ALIGN * _ALIGN + _ALIGN)
                 self.chunks.append(torch.empty(size, device=self.device, dtype=torch.uint8))
-            chunk = self.chunks[self.cur]
-            if self.off + need <= chunk.numel():
-                out = chunk[self.off:self.off + nbytes]
-                self.off += need
-                return out
+            if self.off + need <= self.chunks[self.cur].numel():
+                break
             self.cur += 1
             self.off = 0
-
-    def alloc(self, shape, dtype) -> torch.Tensor:
-        n = math.prod(shape)
-        if n == 0:
-            return torch.empty(shape, device=self.device, dtype=dtype)
-        itemsize = torch.empty(0, dtype=dtype).element_size()
-        return self._raw(n * itemsize).view(dtype).view(shape)
+        # one as_strided on the cached typed view of the chunk (contiguous strides computed here)
+        strides, acc = [], 1
+        for d in reversed(shape):
+            strides.append(acc)
+            acc *= d
+        strides.reverse()
+        out = self._typed(self.cur, dtype).as_strided(shape, strides, self.off // itemsize)
+        self.off += need
+        return out
 
 
 ARENA = StepArena()

@@ -172,6 +172,43 @@ def test_linear_tcgen05_3xfp16(M, N, K):
     assert e(db, dz64.sum(0)) < 1e-5
 
 
+def _split_reference(x: torch.Tensor):
+    """numpy-level restatement of gcbf_amax_f32 + gcbf_split_f16: s = 2^(14 - floor(log2(max|x|))), hi = fp16(x*s),
+    lo = fp16(x*s - hi) (both round-to-nearest-even).  Returns (amax_bits, hi, lo, s)."""
+    amax = x.abs().max()
+    bits = amax.view(torch.int32).item()
+    e = (bits >> 23) & 0xff
+    s = 1.0 if e in (0, 255) else 2.0 ** min(max(14 - (e - 127), 2 - 127), 252 - 127)
+    xs = x * s
+    hi = xs.half()
+    lo = (xs - hi.float()).half()
+    return bits, hi, lo, s
+
+
+@pytest.mark.parametrize('rows,cols,scale', [(300, 260, 1.0), (1000, 2048, 3e-7), (257, 129, 1e4), (64, 8, 1.0), (5, 1027, 2.5e-3)])
+def test_amax_and_fp16_split_bit_exact(rows, cols, scale):
+    """The fp16 [hi | lo] companion is integer-like work: bit-exact against the restatement, including odd column
+    counts (scalar tail), a padded pitch, fused column sums, and the 22-bit reconstruction bound."""
+    x = (torch.randn(rows, cols, generator=_g(rows + cols)) * scale)
+    x[0, 0] = 0.0
+    bits, hi, lo, s = _split_reference(x)
+    xd = x.to(DEV)
+    colsum = torch.empty(cols, device=DEV)
+    h = ops.split_h(xd, colsum=colsum)
+    assert h.amax.item() == bits
+    assert h.ld % 8 == 0 and h.buf.shape == (2, rows, h.ld)
+    assert torch.equal(h.buf[0, :, :cols].cpu(), hi)
+    assert torch.equal(h.buf[1, :, :cols].cpu(), lo)
+    rec = (h.buf[0, :, :cols].double() + h.buf[1, :, :cols].double()).cpu() / s
+    assert ((rec - x.double()).abs() <= x.abs().double() * 2.0 ** -21 + x.abs().max().item() * 2.0 ** -39).all()
+    assert torch.allclose(colsum.cpu().double(), x.double().sum(0), rtol=0, atol=1e-5 * scale * math.sqrt(rows) + 1e-30)
+    # a strided view (leading dimension > cols) gives the same companion
+    big = torch.zeros(rows, cols + 5, device=DEV)
+    big[:, :cols] = xd
+    h2 = ops.split_h(big[:, :cols])
+    assert h2.amax.item() == bits and torch.equal(h2.buf[:, :, :cols], h.buf[:, :, :cols])
+
+
 @pytest.mark.parametrize('M,N,K', [(5000, 2048, 13), (129, 256, 12), (24196, 2048, 14), (1000, 70, 16), (64, 64, 1)])
 def test_linear_skinny_k(M, N, K):
     """In-features <= 16 (first phi layer): dedicated HBM-streaming kernels, exact fp32 FFMA."""
