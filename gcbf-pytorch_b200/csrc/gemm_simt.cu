@@ -223,7 +223,10 @@ __global__ void act_bwd_kernel(const float* __restrict__ dY, const float* __rest
   dZ[i] = d;
 }
 
+int launch_colsum_narrow(const float* dZ, int ld, int M, int N, float* db, int accumulate, cudaStream_t st);
+
 int launch_colsum(const float* dZ, int ld, int M, int N, float* db, int accumulate, cudaStream_t st) {
+  if (N <= 32) return launch_colsum_narrow(dZ, ld, M, N, db, accumulate, st);
   int rsplit = (int)imin64(64, imax64(1, (int64_t)M / 2048));
   int rows_per_block = ceil_div(M, rsplit);
   rsplit = ceil_div(M, rows_per_block);

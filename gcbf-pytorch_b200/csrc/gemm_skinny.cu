@@ -2,8 +2,10 @@
 // (reference gcbf/nn/gnn.py:31, gcbf/nn/mlp.py:44-47).  These are HBM-bound streams over the [M, 2048] side
 // (E x 2048 x 4 B = 198 MB at config C2) with 2*K flops per element, so they get dedicated kernels instead of a
 // 128x128 GEMM tile that would be 90 % padding:
-//   fwd   : Y[M,N]  = act(alpha * X[M,K] W[N,K]^T + b)       thread = output column, X rows broadcast from smem
-//   dgrad : dX[M,K] = alpha * dZ[M,N] W[N,K]                 warp = row, lanes sweep N, shuffle-reduce K sums
+//   fwd   : Y[M,N]  = act(alpha * X[M,K] W[N,K]^T + b)       thread = 4 output columns (16-byte stores), X rows broadcast
+//                                                            from smem; optional fused max|Y| for the next layer's fp16 split
+//   dgrad : dX[M,K] = alpha * dZ[M,N] W[N,K]                 warp = 4 rows, lanes sweep N against W^T staged in smem,
+//                                                            shuffle-reduce the K sums
 //   wgrad : dW[N,K] += alpha * dZ^T X ; db[N] += colsum(dZ)  thread = column n, rows split over blockIdx.y
 #include "common.cuh"
 
@@ -12,17 +14,24 @@ namespace gcbf {
 constexpr int SK = 16;          // max in-features handled here
 constexpr int SK_ROWS = 64;     // rows staged per block iteration
 
+constexpr int SKF_COLS = 4;     // output columns per thread in the forward kernel (one 16-byte store per row)
+
 __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
                                                          int ldw, const float* __restrict__ bias,
                                                          const float* __restrict__ alpha_p, float* __restrict__ Y, int ldy,
-                                                         int M, int N, int K, int act, int rows_per_block) {
+                                                         int M, int N, int K, int act, int rows_per_block,
+                                                         uint32_t* __restrict__ amax_out, int vec_ok) {
   __shared__ __align__(16) float xs[SK_ROWS][SK];
-  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int n0 = (blockIdx.x * 256 + threadIdx.x) * SKF_COLS;
   const float alpha = alpha_p ? __ldg(alpha_p) : 1.f;
-  float w[SK];
+  float w[SKF_COLS][SK], b[SKF_COLS];
 #pragma unroll
-  for (int k = 0; k < SK; ++k) w[k] = (n < N && k < K) ? __ldg(W + (size_t)n * ldw + k) * alpha : 0.f;
-  const float b = (n < N && bias) ? __ldg(bias + n) : 0.f;
+  for (int c = 0; c < SKF_COLS; ++c) {
+#pragma unroll
+    for (int k = 0; k < SK; ++k) w[c][k] = (n0 + c < N && k < K) ? __ldg(W + (size_t)(n0 + c) * ldw + k) * alpha : 0.f;
+    b[c] = (n0 + c < N && bias) ? __ldg(bias + n0 + c) : 0.f;
+  }
+  float ymax = 0.f;
   const int m_begin = blockIdx.y * rows_per_block, m_end = min(M, m_begin + rows_per_block);
   for (int m0 = m_begin; m0 < m_end; m0 += SK_ROWS) {
     __syncthreads();
@@ -31,53 +40,100 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict
       xs[r][k] = (m0 + r < m_end && k < K) ? X[(size_t)(m0 + r) * ldx + k] : 0.f;
     }
     __syncthreads();
-    if (n < N) {
+    if (n0 < N) {
       const int rows = min(SK_ROWS, m_end - m0);
       for (int r = 0; r < rows; ++r) {
         const float4* xr = reinterpret_cast<const float4*>(xs[r]);
-        float acc = 0.f;
+        float y[SKF_COLS];
+#pragma unroll
+        for (int c = 0; c < SKF_COLS; ++c) y[c] = 0.f;
 #pragma unroll
         for (int q = 0; q < SK / 4; ++q) {
           const float4 v = xr[q];
-          acc = fmaf(v.x, w[4 * q], acc); acc = fmaf(v.y, w[4 * q + 1], acc);
-          acc = fmaf(v.z, w[4 * q + 2], acc); acc = fmaf(v.w, w[4 * q + 3], acc);
+#pragma unroll
+          for (int c = 0; c < SKF_COLS; ++c) {
+            y[c] = fmaf(v.x, w[c][4 * q], y[c]); y[c] = fmaf(v.y, w[c][4 * q + 1], y[c]);
+            y[c] = fmaf(v.z, w[c][4 * q + 2], y[c]); y[c] = fmaf(v.w, w[c][4 * q + 3], y[c]);
+          }
         }
-        float y = acc + b;
-        if (act == GCBF_ACT_RELU) y = fmaxf(y, 0.f);
-        else if (act == GCBF_ACT_TANH) y = tanhf(y);
-        Y[(size_t)(m0 + r) * ldy + n] = y;
+#pragma unroll
+        for (int c = 0; c < SKF_COLS; ++c) {
+          y[c] += b[c];
+          if (act == GCBF_ACT_RELU) y[c] = fmaxf(y[c], 0.f);
+          else if (act == GCBF_ACT_TANH) y[c] = tanhf(y[c]);
+          if (n0 + c < N) ymax = fmaxf(ymax, fabsf(y[c]));
+        }
+        float* dst = Y + (size_t)(m0 + r) * ldy + n0;
+        if (vec_ok && n0 + SKF_COLS <= N) {
+          *reinterpret_cast<float4*>(dst) = make_float4(y[0], y[1], y[2], y[3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < SKF_COLS; ++c)
+            if (n0 + c < N) dst[c] = y[c];
+        }
       }
     }
   }
+  if (amax_out) {   // max|Y| for the fp16 split of the next (tensor-core) layer; non-negative floats order like uints
+    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(ymax));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(amax_out, m);
+  }
 }
+
+constexpr int SKD_NCHUNK = 512;   // columns of W staged per pass: [SK][512] floats = 32 KB of shared memory
 
 __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restrict__ dZ, int lddz, const float* __restrict__ W,
                                                            int ldw, const float* __restrict__ alpha_p,
                                                            const float* __restrict__ relu_src, int ld_relu,
-                                                           float* __restrict__ dX, int lddx, int M, int N, int K, int accumulate) {
-  const int m = (blockIdx.x * 256 + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (m >= M) return;
-  float acc[SK];
-#pragma unroll
-  for (int k = 0; k < SK; ++k) acc[k] = 0.f;
-  const float* zrow = dZ + (size_t)m * lddz;
-  for (int n = lane; n < N; n += 32) {
-    const float z = zrow[n];
-    const float* wr = W + (size_t)n * ldw;
-#pragma unroll
-    for (int k = 0; k < SK; ++k)
-      if (k < K) acc[k] = fmaf(z, __ldg(wr + k), acc[k]);
-  }
+                                                           float* __restrict__ dX, int lddx, int M, int N, int K, int accumulate,
+                                                           int rows_per_block) {
+  __shared__ float wt[SK][SKD_NCHUNK + 1];   // W^T chunk: wt[k][n] -> lanes read consecutive n (conflict free)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_begin = blockIdx.x * rows_per_block, m_end = min(M, m_begin + rows_per_block);
   const float alpha = alpha_p ? __ldg(alpha_p) : 1.f;
+  constexpr int RPW = 4;                   // rows per warp per pass (independent accumulators -> loads in flight)
+  for (int mb = m_begin; mb < m_end; mb += 8 * RPW) {
+    float acc[RPW][SK];
 #pragma unroll
-  for (int k = 0; k < SK; ++k) {
-    const float s = warp_sum(acc[k]);
-    if (lane == k && k < K) {
-      float v = alpha * s;
-      if (relu_src && !(relu_src[(size_t)m * ld_relu + k] > 0.f)) v = 0.f;
-      float* dst = dX + (size_t)m * lddx + k;
-      *dst = accumulate ? *dst + v : v;
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int k = 0; k < SK; ++k) acc[r][k] = 0.f;
+    for (int nc = 0; nc < N; nc += SKD_NCHUNK) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < SK * SKD_NCHUNK; i += 256) {
+        const int n = i / SK, k = i % SK;       // consecutive threads read consecutive k of one weight row
+        wt[k][n] = (nc + n < N && k < K) ? __ldg(W + (size_t)(nc + n) * ldw + k) : 0.f;
+      }
+      __syncthreads();
+      const int nlim = min(SKD_NCHUNK, N - nc);
+      for (int n = lane; n < nlim; n += 32) {
+        float z[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          const int m = mb + warp * RPW + r;
+          z[r] = (m < m_end) ? __ldg(dZ + (size_t)m * lddz + nc + n) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < SK; ++k) {
+          const float wv = wt[k][n];
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) acc[r][k] = fmaf(z[r], wv, acc[r][k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int m = mb + warp * RPW + r;
+#pragma unroll
+      for (int k = 0; k < SK; ++k) {
+        const float s = warp_sum(acc[r][k]);
+        if (lane == k && k < K && m < m_end) {
+          float v = alpha * s;
+          if (relu_src && !(relu_src[(size_t)m * ld_relu + k] > 0.f)) v = 0.f;
+          float* dst = dX + (size_t)m * lddx + k;
+          *dst = accumulate ? *dst + v : v;
+        }
+      }
     }
   }
 }
@@ -101,16 +157,21 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
     }
     __syncthreads();
     if (n < N) {
-      const int rows = min(SK_ROWS, m_end - m0);
-      for (int r = 0; r < rows; ++r) {
-        const float z = dZ[(size_t)(m0 + r) * lddz + n];
-        const float4* xr = reinterpret_cast<const float4*>(xs[r]);
-        accb += z;
+      const int rows = min(SK_ROWS, m_end - m0);     // rows beyond `rows` are zero in xs, so reading dZ row 0 for them is harmless
+      for (int r = 0; r < rows; r += 4) {
+        float z[4];
 #pragma unroll
-        for (int q = 0; q < SK / 4; ++q) {
-          const float4 v = xr[q];
-          acc[4 * q] = fmaf(z, v.x, acc[4 * q]); acc[4 * q + 1] = fmaf(z, v.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(z, v.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(z, v.w, acc[4 * q + 3]);
+        for (int u = 0; u < 4; ++u) z[u] = (r + u < rows) ? __ldg(dZ + (size_t)(m0 + r + u) * lddz + n) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4* xr = reinterpret_cast<const float4*>(xs[r + u]);
+          accb += z[u];
+#pragma unroll
+          for (int q = 0; q < SK / 4; ++q) {
+            const float4 v = xr[q];
+            acc[4 * q] = fmaf(z[u], v.x, acc[4 * q]); acc[4 * q + 1] = fmaf(z[u], v.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(z[u], v.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(z[u], v.w, acc[4 * q + 3]);
+          }
         }
       }
     }
@@ -127,20 +188,23 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
 bool skinny_supported(int K) { return K <= SK; }
 
 int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
-                      int ldy, int M, int N, int K, int act, cudaStream_t st) {
-  const int col_blocks = ceil_div(N, 256);
+                      int ldy, int M, int N, int K, int act, uint32_t* amax_out, cudaStream_t st) {
+  const int col_blocks = ceil_div(N, 256 * SKF_COLS);
   int row_blocks = max(1, min(ceil_div(M, SK_ROWS), (4 * kNumSMs) / col_blocks));
   const int rpb = ceil_div(ceil_div(M, row_blocks), SK_ROWS) * SK_ROWS;
   row_blocks = ceil_div(M, rpb);
-  skinny_fwd_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, rpb);
+  const int vec_ok = ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) ? 1 : 0;
+  skinny_fwd_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, rpb,
+                                                                  amax_out, vec_ok);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }
 
 int launch_skinny_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src,
                         int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st) {
-  skinny_dgrad_kernel<<<ceil_div((int64_t)M * 32, 256), 256, 0, st>>>(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx,
-                                                                     M, N, K, accumulate);
+  const int rpb = 32;                       // 8 warps x 4 rows: W^T is staged once per block
+  const int blocks = ceil_div(M, rpb);
+  skinny_dgrad_kernel<<<blocks, 256, 0, st>>>(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, rpb);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }

@@ -54,6 +54,8 @@ struct EpiParams {
   const uint32_t* amax_a;      // device: float bits of max|A|, max|B| (the scales the companions were made with)
   const uint32_t* amax_b;
   uint32_t* amax_out;          // optional: atomicMax of |output| (feeds the next layer's split), or null
+  int tma_store;               // output tile leaves through shared memory + cp.async.bulk.tensor stores (plain overwrite only)
+  int dbg;                     // GCBF_TC_DBG experiments: 1 = skip the global stores of the epilogue, 2 = no TMA stores
 };
 
 // power-of-two scale s with amax*s in [2^14, 2^15); 1 for zero / denormal / non-finite amax
@@ -72,7 +74,8 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int OUT_STAGE_BYTES = 8 * 32 * 128;   // per epilogue warp: one 32 x 32 fp32 chunk of the output tile
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator (256 / 512 columns)
 };
 
@@ -100,12 +103,13 @@ __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, float* __restrict__ C,
-              int ldc, int Mo, int No, int tiles_m, int tiles_n, int kblocks_per_split, int kblocks_total, EpiParams ep) {
+              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+              const __grid_constant__ CUtensorMap map_c, float* __restrict__ C, int ldc, int Mo, int No, int tiles_m, int tiles_n, int kblocks_per_split, int kblocks_total, EpiParams ep) {
   using K = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + K::STAGES * K::STAGE_BYTES);
+  uint8_t* out_stage = smem + K::STAGES * K::STAGE_BYTES;   // 8 x 4 KB, 1024-byte aligned (SWIZZLE_128B boxes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + K::OUT_STAGE_BYTES);
   uint64_t* full = bars;                        // [STAGES]  TMA -> MMA
   uint64_t* empty = bars + K::STAGES;           // [STAGES]  MMA -> TMA
   uint64_t* tfull = bars + 2 * K::STAGES;       // [2]       MMA -> epilogue
@@ -123,6 +127,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b_hi);
     tma_prefetch_desc(&map_b_lo);
+    if (ep.tma_store) tma_prefetch_desc(&map_c);
     for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * 32); }
     fence_barrier_init();
@@ -227,51 +232,75 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           buf ^= 1;
         }
         const int row = m0 + lg * 32 + lane;
-        if (row < Mo) {
+        const bool row_ok = row < Mo;
+        const uint32_t my_stage = smem_u32(out_stage + (warp - 2) * 4096);
 #pragma unroll
-          for (int c = 0; c < CH / 32; ++c) {
-            const int col0 = n0 + chalf * CH + c * 32;
-            if (col0 >= No) continue;
-            float* dst = C + (size_t)row * ldc + col0;
-            const int nv = min(32, No - col0);
-            float v[32];
+        for (int c = 0; c < CH / 32; ++c) {
+          const int col0 = n0 + chalf * CH + c * 32;
+          if (col0 >= No) continue;                            // warp-uniform
+          float* dst = C + (size_t)row * ldc + col0;
+          const int nv = min(32, No - col0);
+          float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = alpha * acc[c * 32 + j];
-            const bool full32 = (nv == 32);
-            if (ep.mode == EPI_FWD) {
-              float bv[32];
-              if (ep.bias && full32 && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15) == 0)) {
+          for (int j = 0; j < 32; ++j) v[j] = alpha * acc[c * 32 + j];
+          const bool full32 = (nv == 32);
+          if (ep.mode == EPI_FWD) {
+            float bv[32];
+            if (ep.bias && full32 && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15) == 0)) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-                  bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) bv[j] = (ep.bias && j < nv) ? __ldg(ep.bias + col0 + j) : 0.f;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
               }
+            } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float y = v[j] + bv[j];
-                if (ep.act == GCBF_ACT_RELU) y = fmaxf(y, 0.f);
-                else if (ep.act == GCBF_ACT_TANH) y = tanhf(y);
-                v[j] = y;
-              }
-            } else if (ep.mode == EPI_DGRAD && ep.relu_src) {
-              const float* ms = ep.relu_src + (size_t)row * ep.ld_relu + col0;
-              if (full32 && ((reinterpret_cast<uintptr_t>(ms) & 15) == 0)) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 m4 = __ldg(reinterpret_cast<const float4*>(ms + j));
-                  v[j] = m4.x > 0.f ? v[j] : 0.f; v[j + 1] = m4.y > 0.f ? v[j + 1] : 0.f;
-                  v[j + 2] = m4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = m4.w > 0.f ? v[j + 3] : 0.f;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nv) v[j] = (__ldg(ms + j) > 0.f) ? v[j] : 0.f;
-              }
+              for (int j = 0; j < 32; ++j) bv[j] = (ep.bias && j < nv) ? __ldg(ep.bias + col0 + j) : 0.f;
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float y = v[j] + bv[j];
+              if (ep.act == GCBF_ACT_RELU) y = fmaxf(y, 0.f);
+              else if (ep.act == GCBF_ACT_TANH) y = tanhf(y);
+              v[j] = y;
+            }
+          } else if (ep.mode == EPI_DGRAD && ep.relu_src && row_ok) {
+            const float* ms = ep.relu_src + (size_t)row * ep.ld_relu + col0;
+            if (full32 && ((reinterpret_cast<uintptr_t>(ms) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(ms + j));
+                v[j] = m4.x > 0.f ? v[j] : 0.f; v[j + 1] = m4.y > 0.f ? v[j + 1] : 0.f;
+                v[j + 2] = m4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = m4.w > 0.f ? v[j + 3] : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) v[j] = (__ldg(ms + j) > 0.f) ? v[j] : 0.f;
+            }
+          }
+          if (ep.dbg & 1) {
+            if (v[0] == 123.456f && row_ok) dst[0] = v[1];
+          } else if (ep.tma_store) {
+            // the 32 x 32 chunk leaves through this warp's shared-memory stage as ONE bulk tensor store: full 128-byte rows,
+            // asynchronous (the warp does not wait on the memory system), ragged edges clipped by the tensor map
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous chunk has left the stage
+            __syncwarp();
+            const uint32_t rbase = my_stage + (uint32_t)(lane * 128);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (uint32_t)(((q ^ (lane & 7)) << 4))), "f"(v[4 * q]),
+                           "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                           : "memory");
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&map_c)),
+                           "r"(my_stage), "r"(col0), "r"(m0 + lg * 32)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else if (row_ok) {
             if (ep.mode == EPI_WGRAD && ep.atomic) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -288,14 +317,15 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
               for (int j = 0; j < 32; ++j)
                 if (j < nv) dst[j] = v[j];
             }
-            if (ep.amax_out) {
+          }
+          if (ep.amax_out && row_ok) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) out_max = fmaxf(out_max, fabsf(v[j]));
-            }
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) out_max = fmaxf(out_max, fabsf(v[j]));
           }
         }
       }
+      if (ep.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       if (ep.amax_out) {
         const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(out_max));   // non-negative floats order like uints
         if (lane == 0 && m) atomicMax(ep.amax_out, m);
@@ -430,11 +460,30 @@ template <int BN, bool A_MN, bool B_MN>
 static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo, int No, int Kc, int splits, EpiParams ep,
                   cudaStream_t st) {
   using K = Cfg<BN>;
-  CUtensorMap mah, mal, mbh, mbl;
+  CUtensorMap mah, mal, mbh, mbl, mc;
   if (int rc = make_map(&mah, A.hi, A.rows, A.cols, A.ld_h, A_MN, BM)) return rc;
   if (int rc = make_map(&mal, A.lo(), A.rows, A.cols, A.ld_h, A_MN, BM)) return rc;
   if (int rc = make_map(&mbh, B.hi, B.rows, B.cols, B.ld_h, B_MN, BN)) return rc;
   if (int rc = make_map(&mbl, B.lo(), B.rows, B.cols, B.ld_h, B_MN, BN)) return rc;
+  static int dbg = -1;
+  if (dbg < 0) { const char* d = getenv("GCBF_TC_DBG"); dbg = d ? atoi(d) : 0; }
+  ep.dbg = dbg;
+  // plain overwrites leave through shared memory + bulk tensor stores (32 x 32 fp32 boxes, SWIZZLE_128B); accumulating /
+  // atomic epilogues and outputs the TMA cannot address (pitch or base not 16-byte aligned) store directly
+  ep.tma_store = (!ep.accumulate && !ep.atomic && !(dbg & 2) && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
+  if (ep.tma_store) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return GCBF_E_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)No, (cuuint64_t)Mo};
+    cuuint64_t strides[1] = {(cuuint64_t)ldc * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d) M=%d N=%d ld=%d", (int)r, Mo, No, ldc); return GCBF_E_CUDA; }
+  } else {
+    mc = mah;   // unused
+  }
   static bool attr_set = false;
   if (!attr_set) {
     GCBF_CUDA_OK(cudaFuncSetAttribute(gemm_h_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
@@ -449,8 +498,8 @@ static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ctas = max(1, min(tiles_m * tiles_n, max(1, sms / nsplit)));
   dim3 grid(ctas, nsplit);
-  gemm_h_kernel<BN, A_MN, B_MN><<<grid, NUM_THREADS, K::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, C, ldc, Mo, No, tiles_m, tiles_n, kps,
-                                                                        kblocks, ep);
+  gemm_h_kernel<BN, A_MN, B_MN><<<grid, NUM_THREADS, K::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, mc, C, ldc, Mo, No, tiles_m, tiles_n,
+                                                                        kps, kblocks, ep);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }

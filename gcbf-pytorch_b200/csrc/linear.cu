@@ -12,7 +12,12 @@ int launch_simt_wgrad(const float* dZ, int lddz, const float* X, int ldx, const 
                       float* db, int M, int N, int K, int accumulate, cudaStream_t st);
 bool skinny_supported(int K);
 int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
-                      int ldy, int M, int N, int K, int act, cudaStream_t st);
+                      int ldy, int M, int N, int K, int act, uint32_t* amax_out, cudaStream_t st);
+bool tiny_supported(int N, int K);
+int launch_tiny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y, int ldy,
+                    int M, int N, int K, int act, cudaStream_t st);
+int launch_tiny_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src,
+                      int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
 int launch_skinny_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src,
                         int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
 int launch_skinny_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw,
@@ -32,21 +37,32 @@ extern "C" int gcbf_has_tcgen05(void) {
 #endif
 }
 
+extern "C" int gcbf_amax_f32(const float* src, int ld, int rows, int cols, void* amax_slot, int accumulate, void* stream);
+
 extern "C" int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias,
                                const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act, int impl,
-                               void* stream) {
+                               void* out_amax, void* stream) {
   GCBF_REQUIRE(M >= 0 && N > 0 && K > 0 && ldx >= K && ldw >= K && ldy >= N, "gcbf_linear_fwd: bad sizes M=%d N=%d K=%d", M, N, K);
   GCBF_REQUIRE(act >= GCBF_ACT_NONE && act <= GCBF_ACT_TANH, "gcbf_linear_fwd: act %d", act);
+  cudaStream_t st = as_stream(stream);
+  if (out_amax) GCBF_CUDA_OK(cudaMemsetAsync(out_amax, 0, 4, st));
   if (M == 0) return GCBF_OK;
   GCBF_REQUIRE(X && W && Y, "gcbf_linear_fwd: null pointer");
-  cudaStream_t st = as_stream(stream);
-  if (impl == 2) { set_error("gcbf_linear_fwd: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  if (impl == 2) { set_error("gcbf_linear_fwd: the tcgen05 path has its own entry point (gcbf_linear_fwd_h)"); return GCBF_E_UNSUPPORTED; }
   if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {   // K <= 16: HBM-bound stream, not a GEMM tile
     g_last_impl = 3;
-    return launch_skinny_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
+    return launch_skinny_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, reinterpret_cast<uint32_t*>(out_amax), st);
   }
-  g_last_impl = 1;
-  return launch_simt_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
+  int rc;
+  if (impl == 0 && tiny_supported(N, K)) {                         // N <= 32: row-streaming kernel
+    g_last_impl = 4;
+    rc = launch_tiny_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
+  } else {
+    g_last_impl = 1;
+    rc = launch_simt_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
+  }
+  if (rc == GCBF_OK && out_amax) rc = gcbf_amax_f32(Y, ldy, M, N, out_amax, 1, stream);
+  return rc;
 }
 
 extern "C" int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma,
@@ -57,10 +73,14 @@ extern "C" int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, i
   if (M == 0) return GCBF_OK;
   GCBF_REQUIRE(dZ && W && dX, "gcbf_linear_bwd_data: null pointer");
   cudaStream_t st = as_stream(stream);
-  if (impl == 2) { set_error("gcbf_linear_bwd_data: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  if (impl == 2) { set_error("gcbf_linear_bwd_data: the tcgen05 path has its own entry point (gcbf_linear_bwd_data_h)"); return GCBF_E_UNSUPPORTED; }
   if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {
     g_last_impl = 3;
     return launch_skinny_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
+  }
+  if (impl == 0 && tiny_supported(N, K)) {
+    g_last_impl = 4;
+    return launch_tiny_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
   }
   g_last_impl = 1;
   return launch_simt_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
@@ -80,7 +100,7 @@ extern "C" int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X,
     return GCBF_OK;
   }
   GCBF_REQUIRE(dZ && X, "gcbf_linear_bwd_weight: null pointer");
-  if (impl == 2) { set_error("gcbf_linear_bwd_weight: tcgen05 path unavailable for M=%d N=%d K=%d", M, N, K); return GCBF_E_UNSUPPORTED; }
+  if (impl == 2) { set_error("gcbf_linear_bwd_weight: the tcgen05 path has its own entry point (gcbf_linear_bwd_weight_h)"); return GCBF_E_UNSUPPORTED; }
   if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {
     g_last_impl = 3;
     return launch_skinny_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);

@@ -32,7 +32,7 @@ _SIGS = {
     'gcbf_edge_attr_fwd': (c_int, [c_int, P, c_int, P, c_int64, P, P]),
     'gcbf_edge_attr_bwd': (c_int, [c_int, P, c_int, P, c_int64, P, P, P]),
     'gcbf_edge_input_fwd': (c_int, [P, c_int, P, c_int, P, c_int64, P, c_int, P]),
-    'gcbf_linear_fwd': (c_int, [P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'gcbf_linear_fwd': (c_int, [P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     'gcbf_linear_bwd_data': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_linear_bwd_weight': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_amax_f32': (c_int, [P, c_int, c_int, c_int, P, c_int, P]),

@@ -96,8 +96,8 @@ class _GNNLayerBase(nn.Module):
             xc, eac, eic = data.x.contiguous(), data.edge_attr.contiguous(), data.edge_index.contiguous()
             ops.call('gcbf_edge_input_fwd', ops.ptr(xc), spec.node_dim, ops.ptr(eac), spec.edge_dim, ops.ptr(eic), E,
                      ops.ptr(ein), ein.shape[1])
-            msg, _ = ops.mlp_forward(ein, spec.phi, False)
-            gate, _ = ops.mlp_forward(msg, spec.gate, False)
+            msg, _, _ = ops.mlp_forward(ein, spec.phi, False)
+            gate, _, _ = ops.mlp_forward(msg, spec.gate, False)
             rowptr = cached_rowptr(data.edge_index, data.x.shape[0])
             att = torch.empty(E, device=ein.device)
             scratch = torch.empty(data.x.shape[0], spec.phi_dim, device=ein.device)

@@ -195,20 +195,20 @@ def linear_bwd_weight_h(dzh: H16, xh: H16, inv_sigma):
     return dW
 
 
-def linear_fwd(x, W, b, inv_sigma, act, out=None):
+def linear_fwd(x, W, b, inv_sigma, act, out=None, out_amax=None):
     x, ldx = _mat(x)
     W, ldw = _mat(W)
     M, K = x.shape
     N = W.shape[0]
     assert W.shape[1] == K, (x.shape, W.shape)
     if use_h(M, N, K):
-        return linear_fwd_h(split_h(x), weight_h(W), b, inv_sigma, act, out=out)
+        return linear_fwd_h(split_h(x), weight_h(W), b, inv_sigma, act, out=out, out_amax=out_amax)
     if out is None:
         out = _empty(M, N, device=x.device, dtype=torch.float32)
     y, ldy = _mat(out)
     assert y.data_ptr() == out.data_ptr()
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_fwd', ptr(x), ldx, ptr(W), ldw, ptr(b), ptr(inv_sigma), ptr(y), ldy,
-                                                 M, N, K, act, GEMM_IMPL))
+                                                 M, N, K, act, GEMM_IMPL, ptr(out_amax)))
     return out
 
 
@@ -398,13 +398,17 @@ class MLPCtx:
     inv_sigma: List[Optional[torch.Tensor]] = field(default_factory=list)
     uv: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = field(default_factory=list)
     acts_h: List[Optional[H16]] = field(default_factory=list)  # acts_h[l] = fp16 companion of acts[l] when layer l is on tcgen05
+    out_amax: Optional[torch.Tensor] = None                   # amax slot of the MLP's output when the caller asked for it
 
 
-def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool) -> Tuple[torch.Tensor, Optional[MLPCtx]]:
+def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool, x_amax: Optional[torch.Tensor] = None,
+                next_width: int = 0):
+    """Returns (y, ctx, y_amax).  `x_amax`: amax slot of x when its producer already reduced it.  `next_width` > 0: the
+    output feeds a linear layer of that many out-features next (possibly in another MLP); if that layer runs on the tensor
+    cores the last layer's epilogue reduces max|y| and the slot is returned as y_amax (else None)."""
     ctx = MLPCtx() if save else None
     if save:
         ctx.acts.append(x)
-    x_amax = None                         # amax of x when the producing GEMM's epilogue already reduced it
     for l, L in enumerate(layers):
         inv_sigma = None
         if L.sn:
@@ -413,29 +417,32 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool) -> Tu
             inv_sigma = sn_power_iter(L.W, L.u, L.v)
         M, K = x.shape
         N = L.W.shape[0]
+        nxt_n = layers[l + 1].W.shape[0] if l + 1 < len(layers) else next_width
+        y_amax = amax_slot(x.device) if (nxt_n > 0 and use_h(M, nxt_n, N)) else None
         xh = None
         if use_h(M, N, K):
             xh = split_h(x, amax=x_amax)
-            nxt = layers[l + 1] if l + 1 < len(layers) else None
-            x_amax = amax_slot(x.device) if (nxt is not None and use_h(M, nxt.W.shape[0], N)) else None
-            x = linear_fwd_h(xh, weight_h(L.W), L.b, inv_sigma, L.act, out_amax=x_amax)
+            x = linear_fwd_h(xh, weight_h(L.W), L.b, inv_sigma, L.act, out_amax=y_amax)
         else:
-            x = linear_fwd(x, L.W, L.b, inv_sigma, L.act)
-            x_amax = None
+            x = linear_fwd(x, L.W, L.b, inv_sigma, L.act, out_amax=y_amax)
+        x_amax = y_amax
         if save:
             ctx.acts.append(x)
             ctx.acts_h.append(xh)
             ctx.inv_sigma.append(inv_sigma)
             ctx.uv.append((L.u.clone(), L.v.clone()) if L.sn else None)
-    return x, ctx
+    return x, ctx, x_amax
 
 
 SKIP_WGRAD = False   # set by GCBF.apply: only input gradients are needed there, weight-gradient GEMMs are skipped
 
 
 def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, need_dx: bool,
-                 dx_out: Optional[torch.Tensor] = None, dx_accumulate: bool = False):
-    """Returns (dx or None, [(dW, db) per layer])."""
+                 dx_out: Optional[torch.Tensor] = None, dx_accumulate: bool = False, dy_amax: Optional[torch.Tensor] = None,
+                 dx_amax: Optional[torch.Tensor] = None):
+    """Returns (dx or None, [(dW, db) per layer]).  `dy_amax`: amax slot of dy when its producer reduced it (only valid if
+    the output layer has no activation).  `dx_amax`: slot that receives max|dx| when the input-gradient GEMM runs on the
+    tensor cores (the caller checks `dx_amax_valid`)."""
     grads = [None] * len(layers)
     dz = dy
     last = len(layers) - 1
@@ -443,7 +450,9 @@ def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, ne
         dz = act_bwd(dz, ctx.acts[last + 1], ACT_TANH)
     elif layers[last].act == ACT_RELU:
         dz = act_bwd(dz, ctx.acts[last + 1], ACT_RELU)
-    dz_amax = None                        # amax of dz when the producing data-grad epilogue already reduced it
+    # amax of dz when the producing data-grad epilogue already reduced it
+    dz_amax = dy_amax if layers[last].act == ACT_NONE else None
+    mlp_backward.dx_amax_valid = False
     for l in range(last, -1, -1):
         L = layers[l]
         x_in = ctx.acts[l]
@@ -471,7 +480,8 @@ def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, ne
                 dz_amax = amax_slot(dz.device) if use_h(M, K, Kp) else None
                 dz = linear_bwd_data_h(dzh, wh, inv_sigma, x_in, out_amax=dz_amax)
             elif need_dx:
-                dz = linear_bwd_data_h(dzh, wh, inv_sigma, None, out=dx_out, accumulate=dx_accumulate)
+                dz = linear_bwd_data_h(dzh, wh, inv_sigma, None, out=dx_out, accumulate=dx_accumulate, out_amax=dx_amax)
+                mlp_backward.dx_amax_valid = dx_amax is not None
             else:
                 dz = None
             continue
@@ -509,7 +519,7 @@ class MLPFunction(torch.autograd.Function):
     def forward(ctx, x, layers, *params):
         _C.require_cuda(x)
         need = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
-        y, mctx = mlp_forward(x.detach(), layers, need)
+        y, mctx, _ = mlp_forward(x.detach(), layers, need)
         ctx.layers, ctx.mctx = layers, mctx
         ctx.need_dx = ctx.needs_input_grad[0]
         return y
@@ -553,8 +563,8 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
     ein = _empty(E, kin, device=dev, dtype=torch.float32)
     call('gcbf_edge_input_fwd', ptr(xc), spec.node_dim, ptr(ea) if E else None, spec.edge_dim, ptr(ei) if E else None,
          E, ptr(ein) if E else None, kin)
-    msg, c_phi = mlp_forward(ein, spec.phi, save)                        # gnn.py:30-32
-    gate, c_gate = mlp_forward(msg, spec.gate, save)                     # AttentionalAggregation.gate_nn
+    msg, c_phi, msg_amax = mlp_forward(ein, spec.phi, save, next_width=spec.gate[0].W.shape[0])   # gnn.py:30-32
+    gate, c_gate, _ = mlp_forward(msg, spec.gate, save, x_amax=msg_amax)  # AttentionalAggregation.gate_nn
     C = spec.phi_dim
     gin_all = _empty(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
     att = _empty(E, device=dev, dtype=torch.float32)
@@ -566,7 +576,9 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
         rows_gather(gin_all, row_index, gin)
     else:
         gin = gin_all
-    feat, c_gamma = mlp_forward(gin, spec.gamma, save)                   # gnn.py:34-36
+    chain_head = spec.head is not None and head_extra is None            # the head reads gamma's output in place
+    feat, c_gamma, feat_amax = mlp_forward(gin, spec.gamma, save,
+                                           next_width=spec.head[0].W.shape[0] if chain_head else 0)   # gnn.py:34-36
     c_head = None
     out = feat
     hin = None
@@ -578,7 +590,7 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
             copy2d(head_extra.contiguous(), hin[:, F:], R, head_extra.shape[1])
         else:
             hin = feat
-        out, c_head = mlp_forward(hin, spec.head, save)
+        out, c_head, _ = mlp_forward(hin, spec.head, save, x_amax=feat_amax if chain_head else None)
     ctx = (c_phi, c_gate, c_gamma, c_head, msg, att, Nn, E) if save else None
     return out, ctx
 
@@ -589,11 +601,15 @@ def net_backward(spec: NetSpec, ctx, d_out, rowptr, row_index, need_d_edge_attr)
     C = spec.phi_dim
     g_head = []
     d_feat = d_out
+    d_feat_amax = None
     if spec.head is not None:
-        d_hin, g_head = mlp_backward(c_head, spec.head, d_out, True)
+        slot = amax_slot(dev)
+        d_hin, g_head = mlp_backward(c_head, spec.head, d_out, True, dx_amax=slot)
         F = spec.gamma[-1].W.shape[0]
         d_feat = d_hin[:, :F] if d_hin.shape[1] != F else d_hin           # strided view: kernels take ld
-    d_gin, g_gamma = mlp_backward(c_gamma, spec.gamma, d_feat, True)
+        if mlp_backward.dx_amax_valid:       # max over all of d_hin >= max over the d_feat columns: a valid (pow2) scale bound
+            d_feat_amax = slot
+    d_gin, g_gamma = mlp_backward(c_gamma, spec.gamma, d_feat, True, dy_amax=d_feat_amax)
     if row_index is not None:
         d_gin_all = _zeros(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
         rows_scatter(d_gin, row_index, d_gin_all)
@@ -604,8 +620,10 @@ def net_backward(spec: NetSpec, ctx, d_out, rowptr, row_index, need_d_edge_attr)
     call('gcbf_attn_aggr_bwd', ptr(msg) if E else None, C, ptr(att) if E else None, ptr(rowptr), Nn, C, ptr(d_gin_all),
          C + spec.node_dim, ptr(d_msg) if E else None, C, ptr(d_gate) if E else None, 0)
     # gate MLP backward; its input gradient is accumulated onto the aggregation's d_msg
-    _, g_gate = mlp_backward(c_gate, spec.gate, d_gate, True, dx_out=d_msg, dx_accumulate=True)
-    d_ein, g_phi = mlp_backward(c_phi, spec.phi, d_msg, need_d_edge_attr)
+    slot = amax_slot(dev)
+    _, g_gate = mlp_backward(c_gate, spec.gate, d_gate, True, dx_out=d_msg, dx_accumulate=True, dx_amax=slot)
+    d_msg_amax = slot if mlp_backward.dx_amax_valid else None            # epilogue max of the accumulated d_msg
+    d_ein, g_phi = mlp_backward(c_phi, spec.phi, d_msg, need_d_edge_attr, dy_amax=d_msg_amax)
     d_edge_attr = None
     if need_d_edge_attr:
         d_edge_attr = d_ein[:, 2 * spec.node_dim:]

@@ -44,7 +44,8 @@ int gcbf_abi_version(void);
 /* 1 if the library was built with the tcgen05 (3xFP16) GEMM path compiled in, else 0 */
 int gcbf_has_tcgen05(void);
 /* which kernel the most recent gcbf_linear_* call on this thread launched: 1 = fp32 SIMT tile GEMM,
- * 3 = fp32 skinny-K stream kernel (in-features <= 16).  (The tcgen05 path has its own entry points, gcbf_linear_*_h.) */
+ * 3 = fp32 skinny-K stream kernel (in-features <= 16), 4 = row-streaming kernel (out-features <= 32).  (The tcgen05 path
+ * has its own entry points, gcbf_linear_*_h.) */
 int gcbf_last_gemm_impl(void);
 
 /* ---------------------------------------------------------------------------------------------------
@@ -92,11 +93,13 @@ int gcbf_edge_input_fwd(const float* x, int node_dim, const float* edge_attr, in
  *   bwd_data  : dX[M,K] (+)= inv_sigma * dZ[M,N] W[N,K]   (* (relu_src[M,K] > 0) if relu_src != NULL)
  *   bwd_weight: dW[N,K] (+)= inv_sigma * dZ[M,N]^T X[M,K] ; db[N] (+)= colsum(dZ)   (db may be NULL)
  *               accumulate != 0 adds into dW/db, otherwise they are overwritten.
- * impl: 0 = auto (skinny-K stream kernel when in-features <= 16, else the SIMT tile kernel), 1 = fp32 SIMT kernel.
+ * impl: 0 = auto (skinny-K stream kernels when in-features <= 16, row-streaming kernels when out-features <= 32,
+ * else the SIMT tile kernel), 1 = fp32 SIMT tile kernel.  fwd's out_amax (optional device uint32) receives the float bits
+ * of max|Y| (for the fp16 split when the next layer runs on the tensor cores).
  * ------------------------------------------------------------------------------------------------- */
 int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias,
                     const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act, int impl,
-                    void* stream);
+                    void* out_amax, void* stream);
 int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma,
                          const float* relu_src, int ld_relu, float* dX, int lddx, int M, int N, int K,
                          int accumulate, int impl, void* stream);

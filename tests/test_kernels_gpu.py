@@ -218,19 +218,47 @@ def test_linear_skinny_k(M, N, K):
     xd, Wd, bd, dzd, rsd = x.to(DEV), W.to(DEV), b.to(DEV), dz.to(DEV), rs.to(DEV)
     alpha = torch.tensor([0.9], device=DEV)
     assert ops.GEMM_IMPL == 0
-    y = ops.linear_fwd(xd, Wd, bd, alpha, ops.ACT_RELU)
-    assert _C.lib().gcbf_last_gemm_impl() == 3
+    am = torch.zeros(1, device=DEV, dtype=torch.int32)
+    y = ops.linear_fwd(xd, Wd, bd, alpha, ops.ACT_RELU, out_amax=am)
+    assert _C.lib().gcbf_last_gemm_impl() == (3 if N >= 64 and M >= 64 else (4 if N <= 32 and K <= 256 else 1))
+    assert am.view(torch.float32).item() == y.abs().max().item()
     dx = ops.linear_bwd_data(dzd, Wd, alpha, rsd)
     dx_acc = torch.ones(M, K, device=DEV)
     ops.linear_bwd_data(dzd, Wd, None, None, out=dx_acc, accumulate=True)
     dW, db = ops.linear_bwd_weight(dzd, xd, alpha)
-    assert _C.lib().gcbf_last_gemm_impl() == 3
     x64, W64, dz64 = xd.double(), Wd.double(), dzd.double()
     e = lambda a, r: ((a.double() - r).abs().max() / r.abs().max()).item()
     assert e(y, torch.relu(0.9 * (x64 @ W64.t()) + bd.double())) < 2e-6
     assert e(dx, 0.9 * (dz64 @ W64) * (rsd > 0)) < 1e-5
     assert e(dx_acc, dz64 @ W64 + 1) < 1e-5
     assert e(dW, 0.9 * (dz64.t() @ x64)) < 1e-5
+    assert e(db, dz64.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize('M,N,K', [(24196, 1, 128), (8192, 32, 128), (8192, 1, 32), (8192, 2, 32), (777, 7, 200), (50, 32, 256), (3, 5, 17)])
+def test_linear_tiny_n(M, N, K):
+    """Out-features <= 32 (gate / head tails): row-streaming fwd and dgrad kernels, narrow column sums; exact fp32 FFMA."""
+    g = _g(M + N + K)
+    x, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
+    dz, rs = torch.randn(M, N, generator=g), torch.randn(M, K, generator=g)
+    xd, Wd, bd, dzd, rsd = x.to(DEV), W.to(DEV), b.to(DEV), dz.to(DEV), rs.to(DEV)
+    alpha = torch.tensor([1.1], device=DEV)
+    assert ops.GEMM_IMPL == 0 and not ops.use_h(M, N, K)
+    am = torch.zeros(1, device=DEV, dtype=torch.int32)
+    y = ops.linear_fwd(xd, Wd, bd, alpha, ops.ACT_TANH, out_amax=am)
+    assert _C.lib().gcbf_last_gemm_impl() == 4
+    dx = ops.linear_bwd_data(dzd, Wd, alpha, rsd)
+    assert _C.lib().gcbf_last_gemm_impl() == 4
+    dx_acc = torch.ones(M, K, device=DEV)
+    ops.linear_bwd_data(dzd, Wd, None, None, out=dx_acc, accumulate=True)
+    dW, db = ops.linear_bwd_weight(dzd, xd, alpha)
+    x64, W64, dz64 = xd.double(), Wd.double(), dzd.double()
+    e = lambda a, r: ((a.double() - r).abs().max() / r.abs().max()).item()
+    assert e(y, torch.tanh(1.1 * (x64 @ W64.t()) + bd.double())) < 2e-6
+    assert am.view(torch.float32).item() == y.abs().max().item()
+    assert e(dx, 1.1 * (dz64 @ W64) * (rsd > 0)) < 2e-6
+    assert e(dx_acc, dz64 @ W64 + 1) < 2e-6
+    assert e(dW, 1.1 * (dz64.t() @ x64)) < 1e-5
     assert e(db, dz64.sum(0)) < 1e-5
 
 
