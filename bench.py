@@ -45,14 +45,46 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons sampled during the timed region.  In-process NVML polling thread (nvidia_ml_py, 20 ms
+    period: an ioctl per sample, no process spawn inside the timed region); falls back to `nvidia-smi -lms 200`."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, None
+        self.thread, self.stop_flag, self.samples, self.reasons, self.max_mhz = None, False, [], set(), None
+
+    def _nvml_loop(self, nv, handle):
+        bits = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+                'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+                'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+                'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(handle))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(',')) else self.index
+            handle = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
@@ -62,6 +94,12 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = self.samples
+            return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': self.max_mhz, 'samples': len(sm),
+                    'reasons': sorted(self.reasons), 'source': 'nvml thread, 20 ms'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.25)
@@ -86,7 +124,7 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.path)
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'reasons': sorted(reasons), 'source': 'nvidia-smi -lms 200'}
 
 
 def build_case(cfg_name, device, rank):

@@ -83,6 +83,90 @@ __global__ void sn_finalize_u_kernel(const float* __restrict__ s, int N, float* 
   if (threadIdx.x == 0) *inv_sigma = 1.f / sigma;
 }
 
+// ---- batched power iteration: every spectral-normalised layer of a net in four launches (blockIdx.z = layer) -------------
+constexpr int kSnMaxBatch = 16;
+struct SnBatch {
+  const float* W[kSnMaxBatch];
+  float* u[kSnMaxBatch];
+  float* v[kSnMaxBatch];
+  float* inv_sigma[kSnMaxBatch];
+  float* partial[kSnMaxBatch];
+  float* s[kSnMaxBatch];
+  int ldw[kSnMaxBatch], N[kSnMaxBatch], K[kSnMaxBatch], rpb[kSnMaxBatch], nsplit[kSnMaxBatch];
+};
+
+__global__ void sn_wt_u_batched_kernel(const __grid_constant__ SnBatch b) {
+  const int l = blockIdx.z;
+  const int N = b.N[l], K = b.K[l], ldw = b.ldw[l], rows_per_block = b.rpb[l];
+  if ((int)blockIdx.y >= b.nsplit[l] || (int)blockIdx.x * 32 >= K) return;
+  const float* __restrict__ W = b.W[l];
+  const float* __restrict__ u = b.u[l];
+  __shared__ float sm[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(N, r0 + rows_per_block);
+  float s = 0.f;
+  if (col < K)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s = fmaf(W[(size_t)r * ldw + col], u[r], s);
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    b.partial[l][(size_t)blockIdx.y * K + col] = t;
+  }
+}
+
+__global__ void sn_finalize_v_batched_kernel(const __grid_constant__ SnBatch b) {
+  const int l = blockIdx.x;
+  const int K = b.K[l], nsplit = b.nsplit[l];
+  const float* __restrict__ partial = b.partial[l];
+  float* __restrict__ v = b.v[l];
+  __shared__ float sm[33];
+  float sq = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < nsplit; ++s) t += partial[(size_t)s * K + k];
+    v[k] = t;
+    sq = fmaf(t, t, sq);
+  }
+  const float nrm = fmaxf(sqrtf(block_sum(sq, sm)), 1e-12f);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) v[k] = v[k] / nrm;
+}
+
+__global__ void sn_w_v_batched_kernel(const __grid_constant__ SnBatch b) {
+  const int l = blockIdx.y;
+  const int N = b.N[l], K = b.K[l], ldw = b.ldw[l];
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* __restrict__ W = b.W[l];
+  const float* __restrict__ v = b.v[l];
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(W[(size_t)row * ldw + k], v[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) b.s[l][row] = acc;
+}
+
+__global__ void sn_finalize_u_batched_kernel(const __grid_constant__ SnBatch b) {
+  const int l = blockIdx.x;
+  const int N = b.N[l];
+  const float* __restrict__ s = b.s[l];
+  float* __restrict__ u = b.u[l];
+  __shared__ float sm[33];
+  float sq = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) sq = fmaf(s[n], s[n], sq);
+  const float nrm = fmaxf(sqrtf(block_sum(sq, sm)), 1e-12f);
+  float dot = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float un = s[n] / nrm;
+    u[n] = un;
+    dot = fmaf(un, s[n], dot);
+  }
+  const float sigma = block_sum(dot, sm);
+  if (threadIdx.x == 0) *b.inv_sigma[l] = 1.f / sigma;
+}
+
 __global__ void dot_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int N, int K,
                            double* __restrict__ out) {
   double acc = 0;
@@ -173,6 +257,43 @@ extern "C" int gcbf_sn_power_iter(const float* W, int ldw, int N, int K, float* 
   GCBF_LAUNCH_OK();
   sn_finalize_u_kernel<<<1, 1024, 0, st>>>(s, N, u, inv_sigma);
   GCBF_LAUNCH_OK();
+  return GCBF_OK;
+}
+
+// Same arithmetic as gcbf_sn_power_iter per layer (bit-identical u, v, 1/sigma), `count` layers per call.  `layers` is a
+// HOST array; workspace_floats >= sum over layers of gcbf_sn_workspace_floats(N, K).
+extern "C" int gcbf_sn_power_iter_batched(const gcbf_sn_layer* layers, int count, float* workspace, size_t workspace_floats,
+                                          void* stream) {
+  GCBF_REQUIRE(layers && count >= 0 && workspace, "gcbf_sn_power_iter_batched: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  size_t off = 0;
+  for (int base = 0; base < count; base += kSnMaxBatch) {
+    const int nb = min(kSnMaxBatch, count - base);
+    SnBatch b{};
+    int max_ct = 0, max_rb = 0;
+    for (int i = 0; i < nb; ++i) {
+      const gcbf_sn_layer& L = layers[base + i];
+      GCBF_REQUIRE(L.W && L.u && L.v && L.inv_sigma && L.N > 0 && L.K > 0 && L.ldw >= L.K, "gcbf_sn_power_iter_batched: layer %d", base + i);
+      const size_t need = gcbf_sn_workspace_floats(L.N, L.K);
+      GCBF_REQUIRE(off + need <= workspace_floats, "gcbf_sn_power_iter_batched: workspace too small");
+      b.W[i] = L.W; b.u[i] = L.u; b.v[i] = L.v; b.inv_sigma[i] = L.inv_sigma; b.ldw[i] = L.ldw; b.N[i] = L.N; b.K[i] = L.K;
+      b.rpb[i] = ceil_div(L.N, kSnRowSplit);
+      b.nsplit[i] = ceil_div(L.N, b.rpb[i]);
+      b.partial[i] = workspace + off;
+      b.s[i] = workspace + off + (size_t)kSnRowSplit * L.K;
+      off += need;
+      max_ct = max(max_ct, ceil_div(L.K, 32));
+      max_rb = max(max_rb, ceil_div((int64_t)L.N * 32, 256));
+    }
+    sn_wt_u_batched_kernel<<<dim3(max_ct, kSnRowSplit, nb), dim3(32, 8), 0, st>>>(b);
+    GCBF_LAUNCH_OK();
+    sn_finalize_v_batched_kernel<<<nb, 1024, 0, st>>>(b);
+    GCBF_LAUNCH_OK();
+    sn_w_v_batched_kernel<<<dim3(max_rb, nb), 256, 0, st>>>(b);
+    GCBF_LAUNCH_OK();
+    sn_finalize_u_batched_kernel<<<nb, 1024, 0, st>>>(b);
+    GCBF_LAUNCH_OK();
+  }
   return GCBF_OK;
 }
 

@@ -20,6 +20,12 @@ class EnvCfg(ctypes.Structure):
                 ('agent_radius', c_double), ('speed_limit', c_double), ('dist2goal', c_double), ('dt', c_double)]
 
 
+class SnLayer(ctypes.Structure):
+    """mirror of `gcbf_sn_layer`"""
+    _fields_ = [('W', c_void_p), ('ldw', c_int32), ('N', c_int32), ('K', c_int32), ('pad_', c_int32), ('u', c_void_p),
+                ('v', c_void_p), ('inv_sigma', c_void_p)]
+
+
 P = c_void_p  # every device pointer travels as void*
 _SIGS = {
     'gcbf_last_error': (c_char_p, []),
@@ -57,6 +63,7 @@ _SIGS = {
     'gcbf_pair_count': (c_int, [P, c_int64, P, c_int64, c_float, P, P]),
     'gcbf_sn_workspace_floats': (c_size_t, [c_int, c_int]),
     'gcbf_sn_power_iter': (c_int, [P, c_int, c_int, c_int, P, P, P, P, P]),
+    'gcbf_sn_power_iter_batched': (c_int, [POINTER(SnLayer), c_int, P, c_size_t, P]),
     'gcbf_sn_grad_fixup': (c_int, [P, c_int, P, c_int, c_int, c_int, P, P, P, P, P]),
     'gcbf_grad_sumsq': (c_int, [P, c_int64, P, P]),
     'gcbf_clip_adam': (c_int, [P, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, c_double, c_int, P]),
@@ -109,7 +116,7 @@ def check(rc, what):
 
 
 # kernels launched by one call of each entry point (for bench.py's `gpu_launches`; memsets are not counted)
-_KERNELS_PER_CALL = {'gcbf_radius_graph_count': 2, 'gcbf_sn_power_iter': 4, 'gcbf_sn_grad_fixup': 2, 'gcbf_linear_bwd_weight': 2,
+_KERNELS_PER_CALL = {'gcbf_radius_graph_count': 2, 'gcbf_sn_power_iter': 4, 'gcbf_sn_power_iter_batched': 4, 'gcbf_sn_grad_fixup': 2, 'gcbf_linear_bwd_weight': 2,
                      'gcbf_linear_h_supported': 0}
 KERNEL_LAUNCHES = 0
 ABI_CALLS = 0

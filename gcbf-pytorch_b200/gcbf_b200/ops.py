@@ -277,6 +277,38 @@ def sn_power_iter(W, u, v):
     return inv_sigma
 
 
+def sn_power_iter_batched(layers) -> list:
+    """One power iteration on every spectral-normalised LinearSpec of `layers` in four launches (instead of four per
+    layer); returns the per-layer 1/sigma device scalars (None for layers without spectral norm)."""
+    sn = [L for L in layers if L.sn]
+    if not sn:
+        return [None] * len(layers)
+    dev = sn[0].W.device
+    inv = torch.empty(len(sn), device=dev, dtype=torch.float32)
+    arr = (_C.SnLayer * len(sn))()
+    need = 0
+    keep = []
+    for i, L in enumerate(sn):
+        Wm, ldw = _mat(L.W)
+        keep.append(Wm)
+        N, K = Wm.shape
+        a = arr[i]
+        a.W, a.ldw, a.N, a.K, a.u, a.v, a.inv_sigma = ptr(Wm), ldw, N, K, ptr(L.u), ptr(L.v), inv.data_ptr() + 4 * i
+        need += int(_C.lib().gcbf_sn_workspace_floats(N, K))
+    ws = _SN_WS.get((dev, 'batched'))
+    if ws is None or ws.numel() < need:
+        ws = _SN_WS[(dev, 'batched')] = torch.empty(max(need, 1 << 18), device=dev, dtype=torch.float32)
+    call('gcbf_sn_power_iter_batched', arr, len(sn), ptr(ws), ws.numel())
+    out, i = [], 0
+    for L in layers:
+        if L.sn:
+            out.append(inv[i:i + 1])
+            i += 1
+        else:
+            out.append(None)
+    return out
+
+
 def sn_grad_fixup(dW, W, u, v, inv_sigma):
     Wm, ldw = _mat(W)
     N, K = Wm.shape
@@ -402,7 +434,7 @@ class MLPCtx:
 
 
 def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool, x_amax: Optional[torch.Tensor] = None,
-                next_width: int = 0):
+                next_width: int = 0, inv_sigmas: Optional[list] = None):
     """Returns (y, ctx, y_amax).  `x_amax`: amax slot of x when its producer already reduced it.  `next_width` > 0: the
     output feeds a linear layer of that many out-features next (possibly in another MLP); if that layer runs on the tensor
     cores the last layer's epilogue reduces max|y| and the slot is returned as y_amax (else None)."""
@@ -413,8 +445,8 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool, x_ama
         inv_sigma = None
         if L.sn:
             # old-style torch spectral_norm in training mode: one power iteration per forward, even under
-            # no_grad (the reference never calls .eval())
-            inv_sigma = sn_power_iter(L.W, L.u, L.v)
+            # no_grad (the reference never calls .eval()); batched per net by the caller when possible
+            inv_sigma = inv_sigmas[l] if inv_sigmas is not None else sn_power_iter(L.W, L.u, L.v)
         M, K = x.shape
         N = L.W.shape[0]
         nxt_n = layers[l + 1].W.shape[0] if l + 1 < len(layers) else next_width
@@ -563,8 +595,13 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
     ein = _empty(E, kin, device=dev, dtype=torch.float32)
     call('gcbf_edge_input_fwd', ptr(xc), spec.node_dim, ptr(ea) if E else None, spec.edge_dim, ptr(ei) if E else None,
          E, ptr(ein) if E else None, kin)
-    msg, c_phi, msg_amax = mlp_forward(ein, spec.phi, save, next_width=spec.gate[0].W.shape[0])   # gnn.py:30-32
-    gate, c_gate, _ = mlp_forward(msg, spec.gate, save, x_amax=msg_amax)  # AttentionalAggregation.gate_nn
+    # the power iterations depend on the weights only: all spectral-normalised layers of the net in one batched call
+    n_phi, n_gate, n_gamma = len(spec.phi), len(spec.gate), len(spec.gamma)
+    isg = sn_power_iter_batched(spec.all_layers())
+    isg_phi, isg_gate = isg[:n_phi], isg[n_phi:n_phi + n_gate]
+    isg_gamma, isg_head = isg[n_phi + n_gate:n_phi + n_gate + n_gamma], isg[n_phi + n_gate + n_gamma:]
+    msg, c_phi, msg_amax = mlp_forward(ein, spec.phi, save, next_width=spec.gate[0].W.shape[0], inv_sigmas=isg_phi)   # gnn.py:30-32
+    gate, c_gate, _ = mlp_forward(msg, spec.gate, save, x_amax=msg_amax, inv_sigmas=isg_gate)  # AttentionalAggregation.gate_nn
     C = spec.phi_dim
     gin_all = _empty(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
     att = _empty(E, device=dev, dtype=torch.float32)
@@ -578,7 +615,7 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
         gin = gin_all
     chain_head = spec.head is not None and head_extra is None            # the head reads gamma's output in place
     feat, c_gamma, feat_amax = mlp_forward(gin, spec.gamma, save,
-                                           next_width=spec.head[0].W.shape[0] if chain_head else 0)   # gnn.py:34-36
+                                           next_width=spec.head[0].W.shape[0] if chain_head else 0, inv_sigmas=isg_gamma)   # gnn.py:34-36
     c_head = None
     out = feat
     hin = None
@@ -590,7 +627,7 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
             copy2d(head_extra.contiguous(), hin[:, F:], R, head_extra.shape[1])
         else:
             hin = feat
-        out, c_head, _ = mlp_forward(hin, spec.head, save, x_amax=feat_amax if chain_head else None)
+        out, c_head, _ = mlp_forward(hin, spec.head, save, x_amax=feat_amax if chain_head else None, inv_sigmas=isg_head)
     ctx = (c_phi, c_gate, c_gamma, c_head, msg, att, Nn, E) if save else None
     return out, ctx
 

@@ -239,6 +239,14 @@ int gcbf_pair_count(const float* hdot, int64_t m_cols, const float* h, int64_t m
 size_t gcbf_sn_workspace_floats(int N, int K);
 int gcbf_sn_power_iter(const float* W, int ldw, int N, int K, float* u, float* v, float* inv_sigma,
                        float* workspace, void* stream);
+/* every spectral-normalised layer of a net in four launches: same arithmetic per layer as gcbf_sn_power_iter
+ * (bit-identical u, v, 1/sigma).  `layers` is a HOST array of `count` descriptors (device pointers inside);
+ * workspace_floats >= sum of gcbf_sn_workspace_floats(N, K) over the layers. */
+typedef struct gcbf_sn_layer {
+  const float* W; int32_t ldw; int32_t N; int32_t K; int32_t pad_; float* u; float* v; float* inv_sigma;
+} gcbf_sn_layer;
+int gcbf_sn_power_iter_batched(const gcbf_sn_layer* layers, int count, float* workspace, size_t workspace_floats,
+                               void* stream);
 int gcbf_sn_grad_fixup(float* dW, int lddw, const float* W, int ldw, int N, int K, const float* u,
                        const float* v, const float* inv_sigma, float* workspace, void* stream);
 

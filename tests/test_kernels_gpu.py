@@ -262,6 +262,27 @@ def test_linear_tiny_n(M, N, K):
     assert e(db, dz64.sum(0)) < 1e-5
 
 
+def test_sn_power_iter_batched_bit_identical():
+    """The batched power iteration (all layers of a net in four launches) must reproduce the per-layer kernels bit for bit."""
+    shapes = [(2048, 13), (2048, 2048), (256, 2048), (128, 256), (1, 128), (512, 1026), (32, 128)]
+    g = _g(5)
+    specs_a, specs_b = [], []
+    for N, K in shapes:
+        W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+        u = torch.nn.functional.normalize(torch.randn(N, generator=g), dim=0).to(DEV)
+        v = torch.nn.functional.normalize(torch.randn(K, generator=g), dim=0).to(DEV)
+        specs_a.append(ops.LinearSpec(W, torch.zeros(N, device=DEV), u.clone(), v.clone()))
+        specs_b.append(ops.LinearSpec(W, torch.zeros(N, device=DEV), u.clone(), v.clone()))
+    specs_b.insert(2, ops.LinearSpec(torch.randn(4, 4, device=DEV), torch.zeros(4, device=DEV)))   # a layer without spectral norm
+    for _ in range(2):
+        want = [ops.sn_power_iter(L.W, L.u, L.v) for L in specs_a]
+        got = ops.sn_power_iter_batched(specs_b)
+        assert got[2] is None
+        got = [x for x in got if x is not None]
+        for La, Lb, a, b in zip(specs_a, [L for L in specs_b if L.sn], want, got):
+            assert torch.equal(La.u, Lb.u) and torch.equal(La.v, Lb.v) and torch.equal(a, b)
+
+
 def test_linear_strided_views():
     """Kernels take leading dimensions: column slices of wider buffers must work without copies."""
     g = _g(9)
