@@ -534,11 +534,11 @@ extern "C" int gcbf_amax_f32(const float* src, int ld, int rows, int cols, void*
 }
 
 extern "C" int gcbf_split_f16(const float* src, int ld, int rows, int cols, const void* amax_slot, void* dst, int ld_h,
-                              float* colsum, void* stream) {
+                              float* colsum, int colsum_accumulate, void* stream) {
   GCBF_REQUIRE(amax_slot && dst && rows >= 0 && cols >= 0 && ld >= cols && ld_h >= cols, "gcbf_split_f16: bad arguments rows=%d cols=%d", rows, cols);
   if (int rc = th::check_plane(dst, ld_h, "gcbf_split_f16")) return rc;
   cudaStream_t st = as_stream(stream);
-  if (colsum) GCBF_CUDA_OK(cudaMemsetAsync(colsum, 0, (size_t)cols * 4, st));
+  if (colsum && !colsum_accumulate) GCBF_CUDA_OK(cudaMemsetAsync(colsum, 0, (size_t)cols * 4, st));
   if (rows == 0 || cols == 0) return GCBF_OK;
   GCBF_REQUIRE(src, "gcbf_split_f16: null src");
   dim3 grid(ceil_div(cols, 64), ceil_div(rows, th::SPLIT_ROWS)), block(32, 8);

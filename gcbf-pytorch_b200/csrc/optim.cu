@@ -186,14 +186,18 @@ __global__ void dot_kernel(const float* __restrict__ A, int lda, const float* __
   }
 }
 
+// dW_orig = dW - <dW, W> * inv_sigma * u v^T (the gradient through sigma of torch spectral_norm).  acc == nullptr: in
+// place on dW; otherwise the corrected gradient is ADDED to acc (the parameter's .grad view) and dW is left alone.
 __global__ void sn_rank1_kernel(float* __restrict__ dW, int lddw, int N, int K, const float* __restrict__ u,
                                 const float* __restrict__ v, const float* __restrict__ inv_sigma,
-                                const double* __restrict__ inner) {
+                                const double* __restrict__ inner, float* __restrict__ acc, int ldacc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N * K) return;
   const int64_t r = i / K, c = i % K;
   const float coef = (float)(*inner) * (*inv_sigma);
-  dW[r * lddw + c] -= coef * u[r] * v[c];
+  const float g = dW[r * lddw + c] - coef * u[r] * v[c];
+  if (acc) acc[r * ldacc + c] += g;
+  else dW[r * lddw + c] = g;
 }
 
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t count, double* __restrict__ out) {
@@ -298,7 +302,8 @@ extern "C" int gcbf_sn_power_iter_batched(const gcbf_sn_layer* layers, int count
 }
 
 extern "C" int gcbf_sn_grad_fixup(float* dW, int lddw, const float* W, int ldw, int N, int K, const float* u,
-                                  const float* v, const float* inv_sigma, float* workspace, void* stream) {
+                                  const float* v, const float* inv_sigma, float* workspace, float* acc, int ldacc,
+                                  void* stream) {
   GCBF_REQUIRE(dW && W && u && v && inv_sigma && workspace && N > 0 && K > 0, "gcbf_sn_grad_fixup: bad arguments");
   GCBF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "gcbf_sn_grad_fixup: workspace must be 8-byte aligned");
   cudaStream_t st = as_stream(stream);
@@ -307,7 +312,8 @@ extern "C" int gcbf_sn_grad_fixup(float* dW, int lddw, const float* W, int ldw, 
   const int64_t total = (int64_t)N * K;
   dot_kernel<<<(int)imin64(ceil_div(total, 256), 4 * kNumSMs), 256, 0, st>>>(dW, lddw, W, ldw, N, K, inner);
   GCBF_LAUNCH_OK();
-  sn_rank1_kernel<<<ceil_div(total, 256), 256, 0, st>>>(dW, lddw, N, K, u, v, inv_sigma, inner);
+  GCBF_REQUIRE(!acc || ldacc >= K, "gcbf_sn_grad_fixup: ldacc");
+  sn_rank1_kernel<<<ceil_div(total, 256), 256, 0, st>>>(dW, lddw, N, K, u, v, inv_sigma, inner, acc, ldacc);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }

@@ -42,7 +42,7 @@ _SIGS = {
     'gcbf_linear_bwd_data': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_linear_bwd_weight': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_amax_f32': (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
-    'gcbf_split_f16': (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, P]),
+    'gcbf_split_f16': (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, c_int, P]),
     'gcbf_linear_h_supported': (c_int, [c_int, c_int, c_int]),
     'gcbf_linear_fwd_h': (c_int, [P, c_int, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     'gcbf_linear_bwd_data_h': (c_int, [P, c_int, P, P, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P]),
@@ -64,7 +64,7 @@ _SIGS = {
     'gcbf_sn_workspace_floats': (c_size_t, [c_int, c_int]),
     'gcbf_sn_power_iter': (c_int, [P, c_int, c_int, c_int, P, P, P, P, P]),
     'gcbf_sn_power_iter_batched': (c_int, [POINTER(SnLayer), c_int, P, c_size_t, P]),
-    'gcbf_sn_grad_fixup': (c_int, [P, c_int, P, c_int, c_int, c_int, P, P, P, P, P]),
+    'gcbf_sn_grad_fixup': (c_int, [P, c_int, P, c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
     'gcbf_grad_sumsq': (c_int, [P, c_int64, P, P]),
     'gcbf_clip_adam': (c_int, [P, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, c_double, c_int, P]),
 }

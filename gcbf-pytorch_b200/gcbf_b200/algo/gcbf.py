@@ -176,7 +176,11 @@ class GCBF(Algorithm):
                 _C.ptr(partial), _C.ptr(d_h), _C.ptr(d_hn), _C.ptr(d_act), _C.ptr(scalars))
 
         bucket.zero_grad()                                               # gcbf.py:220-221
-        torch.autograd.backward([h, h_next, actions], [d_h, d_hn, d_act])  # gcbf.py:222
+        ops.GRAD_INTO_PARAM = True     # weight-grad kernels accumulate straight into the bucket's .grad views
+        try:
+            torch.autograd.backward([h, h_next, actions], [d_h, d_hn, d_act])  # gcbf.py:222
+        finally:
+            ops.GRAD_INTO_PARAM = False
 
         # results leave the arena as private copies (tiny: O(num_agents))
         out = dict(scalars=scalars, h=hd.clone(), actions=actd.clone(), h_next=hnd.clone(), h_next_new=hnnd.clone(),

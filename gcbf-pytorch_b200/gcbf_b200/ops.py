@@ -122,7 +122,7 @@ def amax_slot(device) -> torch.Tensor:
 
 
 def split_h(t: torch.Tensor, amax: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
-            persistent: bool = False, into: Optional[H16] = None) -> H16:
+            persistent: bool = False, into: Optional[H16] = None, colsum_accumulate: bool = False) -> H16:
     """amax (unless the producer already supplied it) + fp16 [hi|lo] split; `colsum` (fp32 [cols]) optionally receives
     the column sums of t (the bias gradient when t = dZ)."""
     m, ld = _mat(t)
@@ -140,7 +140,7 @@ def split_h(t: torch.Tensor, amax: Optional[torch.Tensor] = None, colsum: Option
         if amax is None:
             amax = own_amax
             call('gcbf_amax_f32', ptr(m), ld, rows, cols, ptr(amax), 0)
-        call('gcbf_split_f16', ptr(m), ld, rows, cols, ptr(amax), ptr(buf), ld_h, ptr(colsum))
+        call('gcbf_split_f16', ptr(m), ld, rows, cols, ptr(amax), ptr(buf), ld_h, ptr(colsum), 1 if colsum_accumulate else 0)
     GEMM_TIMER.run_prep(go)
     return H16(buf, amax, rows, cols, ld_h)
 
@@ -186,13 +186,17 @@ def linear_bwd_data_h(dzh: H16, wh: H16, inv_sigma, relu_src, out=None, accumula
     return out
 
 
-def linear_bwd_weight_h(dzh: H16, xh: H16, inv_sigma):
+def linear_bwd_weight_h(dzh: H16, xh: H16, inv_sigma, out=None, accumulate=False):
     M, N, K = dzh.rows, dzh.cols, xh.cols
     assert xh.rows == M
-    dW = _empty(N, K, device=dzh.buf.device, dtype=torch.float32)
+    if out is None:
+        assert not accumulate
+        out = _empty(N, K, device=dzh.buf.device, dtype=torch.float32)
+    o, ldo = _mat(out)
+    assert o.data_ptr() == out.data_ptr() and tuple(o.shape) == (N, K)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_weight_h', ptr(dzh.buf), dzh.ld, ptr(dzh.amax), ptr(xh.buf), xh.ld,
-                                                 ptr(xh.amax), ptr(inv_sigma), ptr(dW), K, M, N, K, 0), impl=2)
-    return dW
+                                                 ptr(xh.amax), ptr(inv_sigma), ptr(o), ldo, M, N, K, 1 if accumulate else 0), impl=2)
+    return out
 
 
 def linear_fwd(x, W, b, inv_sigma, act, out=None, out_amax=None):
@@ -233,18 +237,25 @@ def linear_bwd_data(dz, W, inv_sigma, relu_src, out=None, accumulate=False):
     return out
 
 
-def linear_bwd_weight(dz, x, inv_sigma, need_bias=True):
+def linear_bwd_weight(dz, x, inv_sigma, need_bias=True, out_w=None, out_b=None):
+    """dW, db of one layer.  `out_w` / `out_b`: accumulate INTO these tensors (e.g. the parameters' .grad views) instead of
+    returning fresh ones."""
     dz, lddz = _mat(dz)
     x, ldx = _mat(x)
     M, N = dz.shape
     K = x.shape[1]
     if use_h(M, N, K):
-        db = _empty(N, device=dz.device, dtype=torch.float32) if need_bias else None
-        return linear_bwd_weight_h(split_h(dz, colsum=db), split_h(x), inv_sigma), db
-    dW = _empty(N, K, device=dz.device, dtype=torch.float32)
-    db = _empty(N, device=dz.device, dtype=torch.float32) if need_bias else None
-    GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_weight', ptr(dz), lddz, ptr(x), ldx, ptr(inv_sigma), ptr(dW), K,
-                                                 ptr(db), M, N, K, 0, GEMM_IMPL))
+        db = out_b if out_b is not None else (_empty(N, device=dz.device, dtype=torch.float32) if need_bias else None)
+        dzh = split_h(dz, colsum=db, colsum_accumulate=out_b is not None)
+        return linear_bwd_weight_h(dzh, split_h(x), inv_sigma, out=out_w, accumulate=out_w is not None), db
+    assert (out_w is None) == (out_b is None) or not need_bias
+    acc = out_w is not None
+    dW = out_w if acc else _empty(N, K, device=dz.device, dtype=torch.float32)
+    db = (out_b if acc else _empty(N, device=dz.device, dtype=torch.float32)) if need_bias else None
+    dWm, lddw = _mat(dW)
+    assert dWm.data_ptr() == dW.data_ptr()
+    GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_weight', ptr(dz), lddz, ptr(x), ldx, ptr(inv_sigma), ptr(dW), lddw,
+                                                 ptr(db), M, N, K, 1 if acc else 0, GEMM_IMPL))
     return dW, db
 
 
@@ -309,11 +320,17 @@ def sn_power_iter_batched(layers) -> list:
     return out
 
 
-def sn_grad_fixup(dW, W, u, v, inv_sigma):
+def sn_grad_fixup(dW, W, u, v, inv_sigma, acc=None):
+    """Gradient through sigma of the spectral norm.  acc=None: dW corrected in place; else the corrected gradient is added
+    to `acc` (the parameter's .grad view)."""
     Wm, ldw = _mat(W)
     N, K = Wm.shape
+    am, lda = (None, 0)
+    if acc is not None:
+        am, lda = _mat(acc)
+        assert am.data_ptr() == acc.data_ptr()
     call('gcbf_sn_grad_fixup', ptr(dW), K, ptr(Wm), ldw, N, K, ptr(u), ptr(v), ptr(inv_sigma),
-         ptr(_sn_workspace(W.device, N, K)))
+         ptr(_sn_workspace(W.device, N, K)), ptr(am), lda)
     return dW
 
 
@@ -467,6 +484,17 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool, x_ama
 
 
 SKIP_WGRAD = False   # set by GCBF.apply: only input gradients are needed there, weight-gradient GEMMs are skipped
+GRAD_INTO_PARAM = False   # set by GCBF.train_step: weight / bias gradients are accumulated straight into the parameters'
+#                           .grad views (the flat gradient bucket) by the kernels; autograd then sees None for them
+
+
+def _grad_targets(L):
+    if not GRAD_INTO_PARAM:
+        return None, None
+    gW, gb = getattr(L.W, 'grad', None), getattr(L.b, 'grad', None)
+    if gW is None or gb is None or not gW.is_contiguous() or not gb.is_contiguous():
+        return None, None
+    return gW, gb
 
 
 def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, need_dx: bool,
@@ -494,17 +522,20 @@ def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, ne
         if use_h(M, N, K):
             # one fp16 companion of dz serves the weight-grad (MN-major A) and the data-grad (K-major A); the bias
             # gradient (column sums of dz) is fused into the split
-            db = None if SKIP_WGRAD else _empty(N, device=dz.device, dtype=torch.float32)
-            dzh = split_h(dz, amax=dz_amax, colsum=db)
+            gW, gb = (None, None) if SKIP_WGRAD else _grad_targets(L)
+            db = None if SKIP_WGRAD else (gb if gb is not None else _empty(N, device=dz.device, dtype=torch.float32))
+            dzh = split_h(dz, amax=dz_amax, colsum=db, colsum_accumulate=gb is not None)
             if SKIP_WGRAD:
                 grads[l] = (None, None)
             else:
                 xh = ctx.acts_h[l] if ctx.acts_h[l] is not None else split_h(x_in)
-                dW = linear_bwd_weight_h(dzh, xh, inv_sigma)
                 if L.sn:
+                    dW = linear_bwd_weight_h(dzh, xh, inv_sigma)
                     u, v = ctx.uv[l]
-                    sn_grad_fixup(dW, L.W, u, v, inv_sigma)
-                grads[l] = (dW, db)
+                    sn_grad_fixup(dW, L.W, u, v, inv_sigma, acc=gW)
+                else:
+                    dW = linear_bwd_weight_h(dzh, xh, inv_sigma, out=gW, accumulate=gW is not None)
+                grads[l] = (None if gW is not None else dW, None if gb is not None else db)
             wh = weight_h(L.W)
             if l > 0:
                 assert layers[l - 1].act == ACT_RELU
@@ -521,11 +552,16 @@ def mlp_backward(ctx: MLPCtx, layers: Sequence[LinearSpec], dy: torch.Tensor, ne
         if SKIP_WGRAD:
             grads[l] = (None, None)
         else:
-            dW, db = linear_bwd_weight(dz, x_in, inv_sigma)
+            gW, gb = _grad_targets(L)
             if L.sn:
+                dW, db = linear_bwd_weight(dz, x_in, inv_sigma)
                 u, v = ctx.uv[l]
-                sn_grad_fixup(dW, L.W, u, v, inv_sigma)
-            grads[l] = (dW, db)
+                sn_grad_fixup(dW, L.W, u, v, inv_sigma, acc=gW)
+                if gb is not None:
+                    gb.add_(db)
+            else:
+                dW, db = linear_bwd_weight(dz, x_in, inv_sigma, out_w=gW, out_b=gb)
+            grads[l] = (None if gW is not None else dW, None if gb is not None else db)
         if l > 0:
             # hidden ReLU of layer l-1 folded into the epilogue: dz_{l-1} = (dz_l W_l) * (y_{l-1} > 0)
             assert layers[l - 1].act == ACT_RELU

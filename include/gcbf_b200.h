@@ -120,11 +120,12 @@ int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X, int ldx, c
  *   bwd_weight_h: dW (+)= inv_sigma * dZ^T X                dZ[M,N], X[M,K] companions
  * out_amax (optional, may be NULL): the epilogue atomically maxes |output| into it (zeroed first), which
  * saves the amax pass when the output feeds the next layer's split.  gcbf_split_f16's `colsum`
- * (optional) receives the column sums of the source = the bias gradient when the source is dZ.
+ * (optional) receives the column sums of the source = the bias gradient when the source is dZ
+ * (colsum_accumulate != 0: added to what is there, e.g. the bias's .grad; else overwritten).
  * ------------------------------------------------------------------------------------------------- */
 int gcbf_amax_f32(const float* src, int ld, int rows, int cols, void* amax_slot, int accumulate, void* stream);
 int gcbf_split_f16(const float* src, int ld, int rows, int cols, const void* amax_slot, void* dst, int ld_h,
-                   float* colsum, void* stream);
+                   float* colsum, int colsum_accumulate, void* stream);
 int gcbf_linear_h_supported(int M, int N, int K);
 int gcbf_linear_fwd_h(const void* Xh, int ldxh, const void* x_amax, const void* Wh, int ldwh, const void* w_amax,
                       const float* bias, const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act,
@@ -247,8 +248,10 @@ typedef struct gcbf_sn_layer {
 } gcbf_sn_layer;
 int gcbf_sn_power_iter_batched(const gcbf_sn_layer* layers, int count, float* workspace, size_t workspace_floats,
                                void* stream);
+/* acc == NULL: dW is corrected in place; otherwise the corrected gradient is added to acc[N, K] (pitch ldacc, e.g. the
+ * parameter's .grad view) and dW is left untouched. */
 int gcbf_sn_grad_fixup(float* dW, int lddw, const float* W, int ldw, int N, int K, const float* u,
-                       const float* v, const float* inv_sigma, float* workspace, void* stream);
+                       const float* v, const float* inv_sigma, float* workspace, float* acc, int ldacc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * K8  clip_grad_norm_(max_norm) + Adam on one flat parameter bucket (gcbf/algo/gcbf.py:102-103,
