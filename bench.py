@@ -267,8 +267,21 @@ def run_own(args):
         dist.destroy_process_group()
 
 
+def host_threads():
+    """torch intra-op threads for the CPU legs: the physical cores of the box (torchrun exports OMP_NUM_THREADS=1, which
+    would pin the reference arm to a single core)."""
+    n = max(1, (os.cpu_count() or 2) // 2)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def cpu_sample_step(cfg_name, graphs):
     """Callable running ONE reference train step (oracle port) on the first `graphs` graphs of the config."""
+    host_threads()
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import gcbf_oracle as O                      # the ONLY use of oracle/ in bench.py: the CPU baseline

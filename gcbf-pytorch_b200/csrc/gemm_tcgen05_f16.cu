@@ -68,12 +68,15 @@ __host__ __device__ __forceinline__ uint32_t scale_bits_from_amax(uint32_t amax_
 }
 __host__ __device__ __forceinline__ uint32_t inv_pow2_bits(uint32_t s_bits) { return (uint32_t)(254 - (int)(s_bits >> 23)) << 23; }
 
-template <int BN>
+// CG = cta_group: 1 = one CTA per 128 x BN tile; 2 = a CTA pair per 256 x BN tile (each CTA stages its 128 rows of A and
+// HALF of the B tile; the leader's MMA reads both CTAs' shared memory, so B traffic per output element halves)
+template <int BN, int CG>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;          // one of hi / lo
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / CG;               // B rows (output columns) staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256 && CG == 1) ? 4 : 6;
   static constexpr int OUT_STAGE_BYTES = 8 * 32 * 128;   // per epilogue warp: one 32 x 32 fp32 chunk of the output tile
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator (256 / 512 columns)
@@ -91,21 +94,25 @@ __device__ __forceinline__ uint64_t tile_desc(uint32_t tile_addr, int kk) {
   return make_smem_desc(tile_addr + (uint32_t)(kk * UMMA_K * 2), 16, 8 * BK * 2, BK * 2);
 }
 
-template <bool MN_MAJOR>
+template <bool MN_MAJOR, int CG>
 __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int mn0, int k0, int rows) {
   if (MN_MAJOR) {
-    for (int j = 0; j < rows / MN_BOX; ++j) tma_load_2d(dst + j * (BK * 128), map, bar, mn0 + j * MN_BOX, k0);
+    for (int j = 0; j < rows / MN_BOX; ++j) {
+      if (CG == 2) tma_load_2d_cg2(dst + j * (BK * 128), map, bar, mn0 + j * MN_BOX, k0);
+      else tma_load_2d(dst + j * (BK * 128), map, bar, mn0 + j * MN_BOX, k0);
+    }
   } else {
-    tma_load_2d(dst, map, bar, k0, mn0);
+    if (CG == 2) tma_load_2d_cg2(dst, map, bar, k0, mn0);
+    else tma_load_2d(dst, map, bar, k0, mn0);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
               const __grid_constant__ CUtensorMap map_c, float* __restrict__ C, int ldc, int Mo, int No, int tiles_m, int tiles_n, int kblocks_per_split, int kblocks_total, EpiParams ep) {
-  using K = Cfg<BN>;
+  using K = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* out_stage = smem + K::STAGES * K::STAGE_BYTES;   // 8 x 4 KB, 1024-byte aligned (SWIZZLE_128B boxes)
@@ -120,7 +127,11 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   const int kb0 = blockIdx.y * kblocks_per_split;
   const int kb1 = min(kblocks_total, kb0 + kblocks_per_split);
   const int nkb = kb1 - kb0;
+  // CG == 2: tiles_m counts 256-row pair tiles; this CTA owns rows [pair_m0 + rank * 128, +128) and B rows [n0 + rank * BN/2, +BN/2)
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
   const int num_tiles = tiles_m * tiles_n;
+  const int tile0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -129,15 +140,16 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     tma_prefetch_desc(&map_b_lo);
     if (ep.tma_store) tma_prefetch_desc(&map_c);
     for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * 32); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * CG); }   // one arrive per epilogue warp (of both CTAs)
     fence_barrier_init();
   }
-  if (warp == 1) {            // one warp allocates TMEM and later frees it
-    tmem_alloc(tmem_slot, K::TMEM_COLS);
-    tmem_relinquish();
+  if (warp == 1) {            // one warp (the same one in both CTAs of a pair) allocates TMEM and later frees it
+    if (CG == 2) { tmem_alloc_cg2(tmem_slot, K::TMEM_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, K::TMEM_COLS); tmem_relinquish(); }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -147,36 +159,36 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-          const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+        for (int t = tile0; t < num_tiles; t += tile_stride) {
+          const int m0 = (t / tiles_n) * (BM * CG) + rank * BM, n0 = (t % tiles_n) * BN + rank * K::B_ROWS;
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + stage * K::STAGE_BYTES;
-            mbar_expect_tx(&full[stage], K::STAGE_BYTES);
-            load_tile<A_MN>(st, &map_a_hi, &full[stage], m0, kb * BK, BM);
-            load_tile<A_MN>(st + K::A_BYTES, &map_a_lo, &full[stage], m0, kb * BK, BM);
-            load_tile<B_MN>(st + 2 * K::A_BYTES, &map_b_hi, &full[stage], n0, kb * BK, BN);
-            load_tile<B_MN>(st + 2 * K::A_BYTES + K::B_BYTES, &map_b_lo, &full[stage], n0, kb * BK, BN);
+            if (rank == 0) mbar_expect_tx(&full[stage], CG * K::STAGE_BYTES);   // both CTAs' loads are credited to the leader
+            load_tile<A_MN, CG>(st, &map_a_hi, &full[stage], m0, kb * BK, BM);
+            load_tile<A_MN, CG>(st + K::A_BYTES, &map_a_lo, &full[stage], m0, kb * BK, BM);
+            load_tile<B_MN, CG>(st + 2 * K::A_BYTES, &map_b_hi, &full[stage], n0, kb * BK, K::B_ROWS);
+            load_tile<B_MN, CG>(st + 2 * K::A_BYTES + K::B_BYTES, &map_b_lo, &full[stage], n0, kb * BK, K::B_ROWS);
             if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     } else if (warp == 1) {
       // ===== MMA issuer (single thread) =====
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_f16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      if (lane == 0 && rank == 0) {       // the leader CTA issues for the pair
+        constexpr uint32_t idesc = make_idesc_f16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
         int stage = 0;
         uint32_t phase = 0;
         int buf = 0;
         uint32_t tphase[2] = {0, 0};
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = tile0; t < num_tiles; t += tile_stride) {
           for (int kc = 0; kc < nkb; kc += KCH) {
-            mbar_wait(&tempty[buf], tphase[buf] ^ 1);        // epilogue has drained this accumulator
+            mbar_wait(&tempty[buf], tphase[buf] ^ 1);        // epilogue (of both CTAs) has drained this accumulator
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
             const int kend = min(nkb, kc + KCH);
             for (int kb = kc; kb < kend; ++kb) {
-              mbar_wait(&full[stage], phase);                 // TMA bytes have landed
+              mbar_wait(&full[stage], phase);                 // TMA bytes (of both CTAs) have landed
               tcgen05_fence_after();
               const uint32_t st = smem_u32(smem + stage * K::STAGE_BYTES);
               const uint32_t a_hi = st, a_lo = st + K::A_BYTES, b_hi = st + 2 * K::A_BYTES, b_lo = st + 2 * K::A_BYTES + K::B_BYTES;
@@ -184,14 +196,21 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
               for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                 const uint64_t dah = tile_desc<A_MN>(a_hi, kk), dal = tile_desc<A_MN>(a_lo, kk);
                 const uint64_t dbh = tile_desc<B_MN>(b_hi, kk), dbl = tile_desc<B_MN>(b_lo, kk);
-                umma_f16(d_tmem, dal, dbh, idesc, (kb > kc || kk > 0) ? 1u : 0u);
-                umma_f16(d_tmem, dah, dbl, idesc, 1u);
-                umma_f16(d_tmem, dah, dbh, idesc, 1u);
+                const uint32_t first = (kb > kc || kk > 0) ? 1u : 0u;
+                if (CG == 2) {
+                  umma_f16_cg2(d_tmem, dal, dbh, idesc, first);
+                  umma_f16_cg2(d_tmem, dah, dbl, idesc, 1u);
+                  umma_f16_cg2(d_tmem, dah, dbh, idesc, 1u);
+                } else {
+                  umma_f16(d_tmem, dal, dbh, idesc, first);
+                  umma_f16(d_tmem, dah, dbl, idesc, 1u);
+                  umma_f16(d_tmem, dah, dbh, idesc, 1u);
+                }
               }
-              umma_commit(&empty[stage]);                     // smem slot free once these MMAs retire
+              if (CG == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);   // smem slot free once these MMAs retire
               if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tfull[buf]);                          // chunk sum complete -> epilogue
+            if (CG == 2) umma_commit_cg2(&tfull[buf]); else umma_commit(&tfull[buf]);        // chunk sum complete -> epilogue
             tphase[buf] ^= 1;
             buf ^= 1;
           }
@@ -207,8 +226,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       int buf = 0;
       uint32_t tphase[2] = {0, 0};
       float out_max = 0.f;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      for (int t = tile0; t < num_tiles; t += tile_stride) {
+        const int m0 = (t / tiles_n) * (BM * CG) + rank * BM, n0 = (t % tiles_n) * BN;
         float acc[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) acc[j] = 0.f;
@@ -227,7 +246,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             for (int j = 0; j < 32; ++j) acc[cc * 32 + j] = __fadd_rn(acc[cc * 32 + j], __uint_as_float(r[j]));
           }
           tcgen05_fence_before();
-          mbar_arrive(&tempty[buf]);
+          __syncwarp();
+          if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); }
           tphase[buf] ^= 1;
           buf ^= 1;
         }
@@ -334,9 +354,11 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // neither CTA of a pair may exit (or free TMEM) while the other still signals / reads it
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, K::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, K::TMEM_COLS);
+    else tmem_dealloc(tmem_base, K::TMEM_COLS);
   }
 }
 
@@ -449,6 +471,9 @@ static int make_map(CUtensorMap* map, const __half* base, int rows, int cols, in
   return GCBF_OK;
 }
 
+static int g_dbg = -1;         // GCBF_TC_DBG experiment switches (read once)
+static bool g_two_cta = true;
+
 // companion operand as the GEMM sees it: plane [rows][cols]; K-major: rows = output index, cols = contraction;
 // MN-major: rows = contraction, cols = output index
 struct Operand {
@@ -456,21 +481,19 @@ struct Operand {
   const __half* lo() const { return hi + (size_t)rows * ld_h; }
 };
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo, int No, int Kc, int splits, EpiParams ep,
-                  cudaStream_t st) {
-  using K = Cfg<BN>;
+template <int BN, bool A_MN, bool B_MN, int CG>
+static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int Mo, int No, int Kc, int splits, EpiParams ep,
+                     cudaStream_t st) {
+  using K = Cfg<BN, CG>;
   CUtensorMap mah, mal, mbh, mbl, mc;
   if (int rc = make_map(&mah, A.hi, A.rows, A.cols, A.ld_h, A_MN, BM)) return rc;
   if (int rc = make_map(&mal, A.lo(), A.rows, A.cols, A.ld_h, A_MN, BM)) return rc;
-  if (int rc = make_map(&mbh, B.hi, B.rows, B.cols, B.ld_h, B_MN, BN)) return rc;
-  if (int rc = make_map(&mbl, B.lo(), B.rows, B.cols, B.ld_h, B_MN, BN)) return rc;
-  static int dbg = -1;
-  if (dbg < 0) { const char* d = getenv("GCBF_TC_DBG"); dbg = d ? atoi(d) : 0; }
-  ep.dbg = dbg;
+  if (int rc = make_map(&mbh, B.hi, B.rows, B.cols, B.ld_h, B_MN, K::B_ROWS)) return rc;
+  if (int rc = make_map(&mbl, B.lo(), B.rows, B.cols, B.ld_h, B_MN, K::B_ROWS)) return rc;
+  ep.dbg = g_dbg;
   // plain overwrites leave through shared memory + bulk tensor stores (32 x 32 fp32 boxes, SWIZZLE_128B); accumulating /
   // atomic epilogues and outputs the TMA cannot address (pitch or base not 16-byte aligned) store directly
-  ep.tma_store = (!ep.accumulate && !ep.atomic && !(dbg & 2) && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
+  ep.tma_store = (!ep.accumulate && !ep.atomic && !(g_dbg & 2) && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
   if (ep.tma_store) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return GCBF_E_CUDA; }
@@ -486,22 +509,47 @@ static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    GCBF_CUDA_OK(cudaFuncSetAttribute(gemm_h_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    GCBF_CUDA_OK(cudaFuncSetAttribute(gemm_h_kernel<BN, A_MN, B_MN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles_m = ceil_div(Mo, BM), tiles_n = ceil_div(No, BN);
+  const int tiles_m = ceil_div(Mo, BM * CG), tiles_n = ceil_div(No, BN);   // CG == 2: 256-row pair tiles
   const int kblocks = ceil_div(Kc, BK);
   const int kps = ceil_div(kblocks, splits);
   const int nsplit = ceil_div(kblocks, kps);
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int ctas = max(1, min(tiles_m * tiles_n, max(1, sms / nsplit)));
-  dim3 grid(ctas, nsplit);
-  gemm_h_kernel<BN, A_MN, B_MN><<<grid, NUM_THREADS, K::SMEM_BYTES, st>>>(mah, mal, mbh, mbl, mc, C, ldc, Mo, No, tiles_m, tiles_n,
-                                                                        kps, kblocks, ep);
-  GCBF_LAUNCH_OK();
+  int ctas = max(1, min(tiles_m * tiles_n * CG, max(CG, sms / nsplit)));
+  if (CG == 2) ctas &= ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas, nsplit);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = K::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CG == 2) ? 1 : 0;
+  GCBF_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_h_kernel<BN, A_MN, B_MN, CG>, mah, mal, mbh, mbl, mc, C, ldc, Mo, No, tiles_m, tiles_n, kps,
+                                  kblocks, ep));
   return GCBF_OK;
+}
+
+// CTA pairs (cta_group::2) for the 256-wide tiles unless GCBF_TC_2CTA=0
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo, int No, int Kc, int splits, EpiParams ep,
+                  cudaStream_t st) {
+  if (g_dbg < 0) {
+    const char* d = getenv("GCBF_TC_DBG");
+    g_dbg = d ? atoi(d) : 0;
+    const char* c2 = getenv("GCBF_TC_2CTA");
+    g_two_cta = !(c2 && c2[0] == '0');
+  }
+  if (BN == 256 && g_two_cta) return launch_cg<256, A_MN, B_MN, 2>(A, B, C, ldc, Mo, No, Kc, splits, ep, st);
+  return launch_cg<BN, A_MN, B_MN, 1>(A, B, C, ldc, Mo, No, Kc, splits, ep, st);
 }
 
 static int check_plane(const void* p, int ld_h, const char* what) {

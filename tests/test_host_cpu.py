@@ -131,3 +131,53 @@ def test_dropin_alias():
             "print(g.GCBF.__module__)") % (os.path.join(ROOT, 'gcbf-pytorch_b200'), os.path.join(ROOT, 'gcbf-pytorch_b200', 'dropin'))
     out = subprocess.check_output([sys.executable, '-c', code], text=True)
     assert out.strip() == 'gcbf_b200.algo.gcbf'
+
+
+def test_step_arena_views_are_disjoint_aligned_and_rewound():
+    """The step arena (bump allocator behind every activation of train_step): views must not overlap, must honour
+    dtype and shape, stay 256-byte aligned relative to the chunk, spill into a new chunk when one is full, and
+    begin() must rewind."""
+    import torch
+    from gcbf_b200 import arena
+    A = arena.StepArena()
+    dev = torch.device('cpu')
+    A.begin(dev)
+    ts = [A.alloc((3, 5), torch.float32), A.alloc((7,), torch.int32), A.alloc((2, 4, 8), torch.float16),
+          A.alloc((0, 4), torch.float32), A.alloc((1,), torch.int64)]
+    base = A.chunks[0].data_ptr()
+    spans = []
+    for t in ts:
+        if t.numel() == 0:
+            continue
+        assert t.is_contiguous() and (t.data_ptr() - base) % 256 == 0
+        spans.append((t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    for i, t in enumerate(ts):
+        t.fill_(i + 1)
+    for i, t in enumerate(ts):
+        assert (t == i + 1).all()
+    first = ts[0].data_ptr()
+    big = A.alloc((arena._CHUNK_BYTES // 4 + 10,), torch.float32)     # does not fit the rest of chunk 0 -> new chunk
+    assert len(A.chunks) == 2 and big.numel() == arena._CHUNK_BYTES // 4 + 10
+    A.end()
+    assert A.high_water > arena._CHUNK_BYTES
+    A.begin(dev)
+    assert A.alloc((3, 5), torch.float32).data_ptr() == first
+    A.end()
+
+
+def test_tensor_core_dispatch_rule():
+    """Which layers of the reference's MLPs go to the tcgen05 kernel (host-side rule, no GPU needed)."""
+    from gcbf_b200 import ops
+    assert ops.use_h(24196, 2048, 2048) and ops.use_h(8192, 1024, 2048) and ops.use_h(8192, 2048, 260)
+    assert ops.use_h(24196, 128, 256)                       # gate 256 -> 128
+    assert not ops.use_h(24196, 2048, 12)                   # first phi layer: skinny-K stream kernel
+    assert not ops.use_h(24196, 1, 128) and not ops.use_h(8192, 32, 128)   # tiny-N tails
+    assert not ops.use_h(72, 2048, 2048)                    # too few rows for a 128-row tile to pay off
+    old = ops.GEMM_IMPL
+    try:
+        ops.GEMM_IMPL = 1
+        assert not ops.use_h(24196, 2048, 2048)
+    finally:
+        ops.GEMM_IMPL = old
