@@ -472,7 +472,7 @@ static int make_map(CUtensorMap* map, const __half* base, int rows, int cols, in
 }
 
 static int g_dbg = -1;         // GCBF_TC_DBG experiment switches (read once)
-static bool g_two_cta = false;
+static bool g_two_cta = true;
 
 // companion operand as the GEMM sees it: plane [rows][cols]; K-major: rows = output index, cols = contraction;
 // MN-major: rows = contraction, cols = output index
@@ -546,7 +546,7 @@ static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo,
     const char* d = getenv("GCBF_TC_DBG");
     g_dbg = d ? atoi(d) : 0;
     const char* c2 = getenv("GCBF_TC_2CTA");
-    g_two_cta = (c2 && c2[0] == '1');   // opt-in until validated on hardware
+    g_two_cta = !(c2 && c2[0] == '0');
   }
   if (BN == 256 && g_two_cta) return launch_cg<256, A_MN, B_MN, 2>(A, B, C, ldc, Mo, No, Kc, splits, ep, st);
   return launch_cg<BN, A_MN, B_MN, 1>(A, B, C, ldc, Mo, No, Kc, splits, ep, st);

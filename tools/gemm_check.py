@@ -54,7 +54,7 @@ for (M, N, K) in [(24196, 2048, 2048), (8192, 2048, 2048), (24196, 256, 2048), (
     y = torch.empty(M, N, device=dev); dx = torch.empty(M, K, device=dev)
     fl = 2.0 * M * N * K
     t_amax = timeit(lambda: _C.call('gcbf_amax_f32', x.data_ptr(), K, M, K, am.data_ptr(), 0))
-    t_split = timeit(lambda: _C.call('gcbf_split_f16', x.data_ptr(), K, M, K, xh.amax.data_ptr(), xh.buf.data_ptr(), xh.ld, None))
+    t_split = timeit(lambda: _C.call('gcbf_split_f16', x.data_ptr(), K, M, K, xh.amax.data_ptr(), xh.buf.data_ptr(), xh.ld, None, 0))
     t_f = timeit(lambda: ops.linear_fwd_h(xh, wh, b, None, ops.ACT_RELU, out=y, out_amax=am))
     t_d = timeit(lambda: ops.linear_bwd_data_h(dzh, wh, None, x, out=dx, out_amax=am))
     t_w = timeit(lambda: ops.linear_bwd_weight_h(dzh, xh, None))
