@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
                                                            int ldw, const float* __restrict__ alpha_p,
                                                            const float* __restrict__ relu_src, int ld_relu,
                                                            float* __restrict__ dX, int lddx, int M, int N, int K, int accumulate,
-                                                           int rows_per_block) {
-  __shared__ float wt[SK][SKD_NCHUNK + 1];   // W^T chunk: wt[k][n] -> lanes read consecutive n (conflict free)
+                                                           int rows_per_block, int vec_ok) {
+  __shared__ __align__(16) float wt[SK][SKD_NCHUNK + 4];   // W^T chunk: wt[k][n] -> lanes read consecutive n (16-byte reads, conflict free)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_begin = blockIdx.x * rows_per_block, m_end = min(M, m_begin + rows_per_block);
   const float alpha = alpha_p ? __ldg(alpha_p) : 1.f;
@@ -106,18 +106,37 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
       }
       __syncthreads();
       const int nlim = min(SKD_NCHUNK, N - nc);
-      for (int n = lane; n < nlim; n += 32) {
-        float z[RPW];
+      if (vec_ok && (nlim & 3) == 0) {
+        for (int n = lane * 4; n < nlim; n += 128) {       // 16-byte loads: 512 B of a dZ row per warp instruction
+          float4 z[RPW];
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-          const int m = mb + warp * RPW + r;
-          z[r] = (m < m_end) ? __ldg(dZ + (size_t)m * lddz + nc + n) : 0.f;
+          for (int r = 0; r < RPW; ++r) {
+            const int m = mb + warp * RPW + r;
+            z[r] = (m < m_end) ? __ldg(reinterpret_cast<const float4*>(dZ + (size_t)m * lddz + nc + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < SK; ++k) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&wt[k][n]);
+            const float w0 = w4.x, w1 = w4.y, w2 = w4.z, w3 = w4.w;
+#pragma unroll
+            for (int r = 0; r < RPW; ++r)
+              acc[r][k] = fmaf(z[r].w, w3, fmaf(z[r].z, w2, fmaf(z[r].y, w1, fmaf(z[r].x, w0, acc[r][k]))));
+          }
         }
+      } else {
+        for (int n = lane; n < nlim; n += 32) {
+          float z[RPW];
 #pragma unroll
-        for (int k = 0; k < SK; ++k) {
-          const float wv = wt[k][n];
+          for (int r = 0; r < RPW; ++r) {
+            const int m = mb + warp * RPW + r;
+            z[r] = (m < m_end) ? __ldg(dZ + (size_t)m * lddz + nc + n) : 0.f;
+          }
 #pragma unroll
-          for (int r = 0; r < RPW; ++r) acc[r][k] = fmaf(z[r], wv, acc[r][k]);
+          for (int k = 0; k < SK; ++k) {
+            const float wv = wt[k][n];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) acc[r][k] = fmaf(z[r], wv, acc[r][k]);
+          }
         }
       }
     }
@@ -158,12 +177,12 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
     __syncthreads();
     if (n < N) {
       const int rows = min(SK_ROWS, m_end - m0);     // rows beyond `rows` are zero in xs, so reading dZ row 0 for them is harmless
-      for (int r = 0; r < rows; r += 4) {
-        float z[4];
+      for (int r = 0; r < rows; r += 8) {
+        float z[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) z[u] = (r + u < rows) ? __ldg(dZ + (size_t)(m0 + r + u) * lddz + n) : 0.f;
+        for (int u = 0; u < 8; ++u) z[u] = (r + u < rows) ? __ldg(dZ + (size_t)(m0 + r + u) * lddz + n) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const float4* xr = reinterpret_cast<const float4*>(xs[r + u]);
           accb += z[u];
 #pragma unroll
@@ -190,7 +209,7 @@ bool skinny_supported(int K) { return K <= SK; }
 int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
                       int ldy, int M, int N, int K, int act, uint32_t* amax_out, cudaStream_t st) {
   const int col_blocks = ceil_div(N, 256 * SKF_COLS);
-  int row_blocks = max(1, min(ceil_div(M, SK_ROWS), (4 * kNumSMs) / col_blocks));
+  int row_blocks = max(1, min(ceil_div(M, SK_ROWS), (12 * kNumSMs) / col_blocks));   // ~6 resident blocks per SM hide the X-tile loads
   const int rpb = ceil_div(ceil_div(M, row_blocks), SK_ROWS) * SK_ROWS;
   row_blocks = ceil_div(M, rpb);
   const int vec_ok = ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) ? 1 : 0;
@@ -204,7 +223,8 @@ int launch_skinny_dgrad(const float* dZ, int lddz, const float* W, int ldw, cons
                         int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st) {
   const int rpb = 32;                       // 8 warps x 4 rows: W^T is staged once per block
   const int blocks = ceil_div(M, rpb);
-  skinny_dgrad_kernel<<<blocks, 256, 0, st>>>(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, rpb);
+  const int vec_ok = ((lddz & 3) == 0 && (reinterpret_cast<uintptr_t>(dZ) & 15) == 0) ? 1 : 0;
+  skinny_dgrad_kernel<<<blocks, 256, 0, st>>>(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, rpb, vec_ok);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }

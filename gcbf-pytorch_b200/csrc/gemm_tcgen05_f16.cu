@@ -34,7 +34,11 @@ namespace th {
 using namespace ptx;
 
 constexpr int BM = 128;
-constexpr int BK = 32;                 // K elements per k-block (= one smem stage)
+#ifndef GCBF_TH_BK
+#define GCBF_TH_BK 32
+#endif
+constexpr int BK = GCBF_TH_BK;         // K elements per k-block (= one smem stage): 32 (64-byte K-major rows) or 64 (128-byte rows)
+static_assert(BK == 32 || BK == 64, "BK must be 32 or 64");
 constexpr int UMMA_K = 16;             // fp16: 32 bytes of K per instruction
 constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 promotion / epilogue
 constexpr int KCH = 256 / BK;          // k-blocks accumulated inside the tensor core before promotion to registers
@@ -76,8 +80,9 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CG;               // B rows (output columns) staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 256 && CG == 1) ? 4 : 6;
   static constexpr int OUT_STAGE_BYTES = 8 * 32 * 128;   // per epilogue warp: one 32 x 32 fp32 chunk of the output tile
+  static constexpr int STAGES_FIT = (232448 - OUT_STAGE_BYTES - 1024 - 256) / STAGE_BYTES;   // 227 KB per CTA
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator (256 / 512 columns)
 };
@@ -462,7 +467,7 @@ static int make_map(CUtensorMap* map, const __half* base, int rows, int cols, in
   cuuint32_t box[2] = {(cuuint32_t)(mn_major ? MN_BOX : BK), (cuuint32_t)(mn_major ? BK : tile_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, (mn_major || BK == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d mn=%d", (int)r, rows, cols, ld_h, (int)mn_major);

@@ -10,7 +10,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgcbf_b200.so')
+LIB_PATH = os.environ.get('GCBF_B200_LIB') or os.path.join(_HERE, 'libgcbf_b200.so')   # (override: kernel experiments)
 _lib = None
 
 

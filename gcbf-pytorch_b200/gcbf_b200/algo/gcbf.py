@@ -128,6 +128,14 @@ class GCBF(Algorithm):
             red = self._red = Reducer(self.process_group)
         return red
 
+    def _side_stream(self, dev):
+        if os.environ.get('GCBF_TWO_STREAMS', '1') == '0':
+            return None
+        st = getattr(self, '_side', None)
+        if st is None:
+            st = self._side = torch.cuda.Stream(device=dev)
+        return st
+
     def train_step(self, graphs, apply_optim: bool = True, compute_acc_h_dot: bool = True) -> Dict[str, Tensor]:
         """One inner iteration of GCBF.update (gcbf.py:158-226) on a collated batch.  Returns device tensors
         (no host sync): 'scalars' = [loss_unsafe, loss_safe, loss_h_dot, loss_action, acc_unsafe, acc_safe,
@@ -148,8 +156,19 @@ class GCBF(Algorithm):
         M = graphs.u_ref.shape[0]
         a_dim = self.action_dim
 
-        h = self.cbf(graphs)                                             # gcbf.py:161  (power iteration #1)
-        actions = self.actor(graphs)                                     # gcbf.py:162
+        # h and the actor's actions are independent: the actor's forward (and, through autograd's stream bookkeeping, its
+        # backward) runs on a side stream so its kernels fill the CBF net's wave tails (GCBF_TWO_STREAMS=0 disables)
+        side = self._side_stream(dev)
+        if side is not None:
+            main = torch.cuda.current_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                actions = self.actor(graphs)                             # gcbf.py:162
+            h = self.cbf(graphs)                                         # gcbf.py:161  (power iteration #1)
+            main.wait_stream(side)
+        else:
+            h = self.cbf(graphs)                                         # gcbf.py:161  (power iteration #1)
+            actions = self.actor(graphs)                                 # gcbf.py:162
         masks = env._masks(graphs)                                       # gcbf.py:168, 180 -- one launch
         graphs_next = env.forward_graph(graphs, actions)                 # gcbf.py:193
         h_next = self.cbf(graphs_next)                                   # gcbf.py:194  (power iteration #2)
@@ -181,6 +200,10 @@ class GCBF(Algorithm):
             torch.autograd.backward([h, h_next, actions], [d_h, d_hn, d_act])  # gcbf.py:222
         finally:
             ops.GRAD_INTO_PARAM = False
+        if side is not None:
+            # the actor's weight-grad kernels wrote into the bucket on the side stream and return no tensors to autograd, so
+            # nothing else orders them before the all-reduce / clip+Adam below
+            torch.cuda.current_stream(dev).wait_stream(side)
 
         # results leave the arena as private copies (tiny: O(num_agents))
         out = dict(scalars=scalars, h=hd.clone(), actions=actd.clone(), h_next=hnd.clone(), h_next_new=hnnd.clone(),

@@ -1,1 +1,2 @@
-for c in 0 1; do echo "=== GCBF_TC_2CTA=$c"; GCBF_TC_2CTA=$c timeout 150 python tools/gemm_check.py 2>&1 | grep -E "^\[|FAILED|Error" | cut -c1-250; done
+for t in 0 1; do echo "=== GCBF_TWO_STREAMS=$t"; GCBF_TWO_STREAMS=$t python tools/dp_timing.py 2>&1 | grep -E "plain "; done
+GCBF_TWO_STREAMS=1 python -m pytest tests/test_parity_gpu.py -q -x 2>&1 | tail -2
