@@ -171,11 +171,25 @@ class GCBF(Algorithm):
             actions = self.actor(graphs)                                 # gcbf.py:162
         masks = env._masks(graphs)                                       # gcbf.py:168, 180 -- one launch
         graphs_next = env.forward_graph(graphs, actions)                 # gcbf.py:193
+        if side is not None:
+            inputs_ready = torch.cuda.Event()
+            inputs_ready.record()                                        # actions / graphs_next exist from here on
         h_next = self.cbf(graphs_next)                                   # gcbf.py:194  (power iteration #2)
-        with torch.no_grad():                                            # gcbf.py:195-201, batched
-            st_relink = env.next_states_single(graphs, actions)
-            relinked = env.add_communication_links(env.make_graph(st_relink))
-            h_next_new = self.cbf(relinked)                              # power iteration #3, value only
+        # the re-linked graph's value-only pass (gcbf.py:195-201, batched) overlaps h_next's forward on the side stream; its
+        # host sync (edge count) then waits for the side stream only, and ops.sn_power_iter_batched keeps power iteration #3
+        # behind #2
+        with torch.no_grad():
+            if side is not None:
+                side.wait_event(inputs_ready)
+                with torch.cuda.stream(side):
+                    st_relink = env.next_states_single(graphs, actions)
+                    relinked = env.add_communication_links(env.make_graph(st_relink))
+                    h_next_new = self.cbf(relinked)                      # power iteration #3, value only
+                torch.cuda.current_stream(dev).wait_stream(side)
+            else:
+                st_relink = env.next_states_single(graphs, actions)
+                relinked = env.add_communication_links(env.make_graph(st_relink))
+                h_next_new = self.cbf(relinked)                          # power iteration #3, value only
 
         partial = torch.empty(16, device=dev, dtype=torch.float64)
         hdot = torch.empty(M, device=dev, dtype=torch.float32)

@@ -288,13 +288,23 @@ def sn_power_iter(W, u, v):
     return inv_sigma
 
 
-def sn_power_iter_batched(layers) -> list:
+_SN_ORDER = {}     # id(first u buffer of a net) -> CUDA event recorded after the net's latest power iteration (+ u/v snapshots)
+
+
+def sn_power_iter_batched(layers, snapshot: bool = False):
     """One power iteration on every spectral-normalised LinearSpec of `layers` in four launches (instead of four per
-    layer); returns the per-layer 1/sigma device scalars (None for layers without spectral norm)."""
+    layer).  Returns (inv_sigmas, uvs): per-layer 1/sigma device scalars (None for layers without spectral norm) and, with
+    `snapshot`, per-layer (u, v) copies taken right after the iteration (the backward's sigma-gradient needs the vectors of
+    ITS forward).  The iterations of one net are chained through a CUDA event, so forwards of the same net issued on
+    different streams still advance u, v in program order (and never overwrite them under a snapshot in flight)."""
     sn = [L for L in layers if L.sn]
     if not sn:
-        return [None] * len(layers)
+        return [None] * len(layers), [None] * len(layers)
     dev = sn[0].W.device
+    key = id(sn[0].u)
+    prev = _SN_ORDER.get(key)
+    if prev is not None:
+        torch.cuda.current_stream(dev).wait_event(prev)
     inv = torch.empty(len(sn), device=dev, dtype=torch.float32)
     arr = (_C.SnLayer * len(sn))()
     need = 0
@@ -306,18 +316,25 @@ def sn_power_iter_batched(layers) -> list:
         a = arr[i]
         a.W, a.ldw, a.N, a.K, a.u, a.v, a.inv_sigma = ptr(Wm), ldw, N, K, ptr(L.u), ptr(L.v), inv.data_ptr() + 4 * i
         need += int(_C.lib().gcbf_sn_workspace_floats(N, K))
-    ws = _SN_WS.get((dev, 'batched'))
+    stream_key = (dev, 'batched', _C.stream())          # one workspace per stream: two forwards may be in flight
+    ws = _SN_WS.get(stream_key)
     if ws is None or ws.numel() < need:
-        ws = _SN_WS[(dev, 'batched')] = torch.empty(max(need, 1 << 18), device=dev, dtype=torch.float32)
+        ws = _SN_WS[stream_key] = torch.empty(max(need, 1 << 18), device=dev, dtype=torch.float32)
     call('gcbf_sn_power_iter_batched', arr, len(sn), ptr(ws), ws.numel())
-    out, i = [], 0
+    snaps = [(L.u.clone(), L.v.clone()) for L in sn] if snapshot else [None] * len(sn)
+    ev = torch.cuda.Event()
+    ev.record()
+    _SN_ORDER[key] = ev
+    out, uvs, i = [], [], 0
     for L in layers:
         if L.sn:
             out.append(inv[i:i + 1])
+            uvs.append(snaps[i])
             i += 1
         else:
             out.append(None)
-    return out
+            uvs.append(None)
+    return out, uvs
 
 
 def sn_grad_fixup(dW, W, u, v, inv_sigma, acc=None):
@@ -451,7 +468,7 @@ class MLPCtx:
 
 
 def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool, x_amax: Optional[torch.Tensor] = None,
-                next_width: int = 0, inv_sigmas: Optional[list] = None):
+                next_width: int = 0, inv_sigmas: Optional[list] = None, uvs: Optional[list] = None):
     """Returns (y, ctx, y_amax).  `x_amax`: amax slot of x when its producer already reduced it.  `next_width` > 0: the
     output feeds a linear layer of that many out-features next (possibly in another MLP); if that layer runs on the tensor
     cores the last layer's epilogue reduces max|y| and the slot is returned as y_amax (else None)."""
@@ -479,7 +496,7 @@ def mlp_forward(x: torch.Tensor, layers: Sequence[LinearSpec], save: bool, x_ama
             ctx.acts.append(x)
             ctx.acts_h.append(xh)
             ctx.inv_sigma.append(inv_sigma)
-            ctx.uv.append((L.u.clone(), L.v.clone()) if L.sn else None)
+            ctx.uv.append((uvs[l] if uvs is not None else (L.u.clone(), L.v.clone())) if L.sn else None)
     return x, ctx, x_amax
 
 
@@ -633,11 +650,13 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
          E, ptr(ein) if E else None, kin)
     # the power iterations depend on the weights only: all spectral-normalised layers of the net in one batched call
     n_phi, n_gate, n_gamma = len(spec.phi), len(spec.gate), len(spec.gamma)
-    isg = sn_power_iter_batched(spec.all_layers())
+    isg, uvs = sn_power_iter_batched(spec.all_layers(), snapshot=save)
     isg_phi, isg_gate = isg[:n_phi], isg[n_phi:n_phi + n_gate]
     isg_gamma, isg_head = isg[n_phi + n_gate:n_phi + n_gate + n_gamma], isg[n_phi + n_gate + n_gamma:]
-    msg, c_phi, msg_amax = mlp_forward(ein, spec.phi, save, next_width=spec.gate[0].W.shape[0], inv_sigmas=isg_phi)   # gnn.py:30-32
-    gate, c_gate, _ = mlp_forward(msg, spec.gate, save, x_amax=msg_amax, inv_sigmas=isg_gate)  # AttentionalAggregation.gate_nn
+    uv_phi, uv_gate = uvs[:n_phi], uvs[n_phi:n_phi + n_gate]
+    uv_gamma, uv_head = uvs[n_phi + n_gate:n_phi + n_gate + n_gamma], uvs[n_phi + n_gate + n_gamma:]
+    msg, c_phi, msg_amax = mlp_forward(ein, spec.phi, save, next_width=spec.gate[0].W.shape[0], inv_sigmas=isg_phi, uvs=uv_phi)   # gnn.py:30-32
+    gate, c_gate, _ = mlp_forward(msg, spec.gate, save, x_amax=msg_amax, inv_sigmas=isg_gate, uvs=uv_gate)  # AttentionalAggregation.gate_nn
     C = spec.phi_dim
     gin_all = _empty(Nn, C + spec.node_dim, device=dev, dtype=torch.float32)
     att = _empty(E, device=dev, dtype=torch.float32)
@@ -651,7 +670,8 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
         gin = gin_all
     chain_head = spec.head is not None and head_extra is None            # the head reads gamma's output in place
     feat, c_gamma, feat_amax = mlp_forward(gin, spec.gamma, save,
-                                           next_width=spec.head[0].W.shape[0] if chain_head else 0, inv_sigmas=isg_gamma)   # gnn.py:34-36
+                                           next_width=spec.head[0].W.shape[0] if chain_head else 0, inv_sigmas=isg_gamma,
+                                           uvs=uv_gamma)   # gnn.py:34-36
     c_head = None
     out = feat
     hin = None
@@ -663,7 +683,7 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
             copy2d(head_extra.contiguous(), hin[:, F:], R, head_extra.shape[1])
         else:
             hin = feat
-        out, c_head, _ = mlp_forward(hin, spec.head, save, x_amax=feat_amax if chain_head else None, inv_sigmas=isg_head)
+        out, c_head, _ = mlp_forward(hin, spec.head, save, x_amax=feat_amax if chain_head else None, inv_sigmas=isg_head, uvs=uv_head)
     ctx = (c_phi, c_gate, c_gamma, c_head, msg, att, Nn, E) if save else None
     return out, ctx
 

@@ -276,7 +276,7 @@ def test_sn_power_iter_batched_bit_identical():
     specs_b.insert(2, ops.LinearSpec(torch.randn(4, 4, device=DEV), torch.zeros(4, device=DEV)))   # a layer without spectral norm
     for _ in range(2):
         want = [ops.sn_power_iter(L.W, L.u, L.v) for L in specs_a]
-        got = ops.sn_power_iter_batched(specs_b)
+        got, _ = ops.sn_power_iter_batched(specs_b)
         assert got[2] is None
         got = [x for x in got if x is not None]
         for La, Lb, a, b in zip(specs_a, [L for L in specs_b if L.sn], want, got):
