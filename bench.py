@@ -255,6 +255,30 @@ def run_own(args):
                 'prep_share_of_step': round(gemm.get('prep_ms', 0.0) / ms_instr, 4),
                 'instrumented_ms_per_step': round(ms_instr / args.steps, 4),
                 'instrumented_pass': 'single stream, CUDA-event pair per GEMM / operand-prep launch', 'traffic': None}
+    dom = gemm.get('dominant')
+    if dom:
+        # the launch shape that takes the most GEMM time: algorithmic FLOPs and bytes per launch (companions in: 2 planes x
+        # 2 B per element of each operand; fp32 out) against its CUDA-event duration; DRAM traffic of exactly this launch shape
+        # from the committed `ncu --set full` capture (profiles/), not from this run
+        M_, N_, K_ = dom['M'], dom['N'], dom['K']
+        out_elems = {'forward': M_ * N_, 'data-grad': M_ * K_, 'weight-grad': N_ * K_}[dom['product']]
+        in_elems = {'forward': M_ * K_ + N_ * K_, 'data-grad': M_ * N_ + N_ * K_, 'weight-grad': M_ * N_ + M_ * K_}[dom['product']]
+        alg_bytes = 4 * in_elems + 4 * out_elems
+        tf = dom['flops_per_launch'] / dom['ms_per_launch'] / 1e9
+        roofline['dominant_launch'] = {
+            'shape': f"{dom['product']} M={M_} N={N_} K={K_}", 'launches': dom['launches'],
+            'flops_per_launch': dom['flops_per_launch'], 'ms_per_launch': round(dom['ms_per_launch'], 4),
+            'achieved': round(tf, 1), 'frac': round(tf / f16_peak, 4), 'frac_issued': round(3 * tf / f16_peak, 4),
+            'algorithmic_bytes_per_launch': alg_bytes}
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r01_gemm_h_ncu_full.json')) as f:
+                cap = json.load(f)['launches'][0]
+            rd, wr = float(cap['dram_read'].split()[0]), float(cap['dram_write'].split()[0])
+            roofline['traffic'] = round((rd + wr) * 1e6)
+            roofline['traffic_source'] = ('dram__bytes_read.sum + dram__bytes_write.sum of one forward M=24196 N=2048 K=2048 launch, '
+                                          'profiles/r01_gemm_h_ncu_full.json (ncu --set full)')
+        except Exception:
+            pass
     line = {
         'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': round(ms / args.steps, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

@@ -40,14 +40,14 @@ class _GemmTimer:
     def disable(self):
         self.on, self.records, self.prep = False, [], []
 
-    def run(self, flops, fn, impl=None):
+    def run(self, flops, fn, impl=None, tag=None):
         if not self.on:
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
-        self.records.append((e0, e1, flops, impl if impl is not None else _C.lib().gcbf_last_gemm_impl()))
+        self.records.append((e0, e1, flops, impl if impl is not None else _C.lib().gcbf_last_gemm_impl(), tag))
 
     def run_prep(self, fn):
         if not self.on:
@@ -61,16 +61,27 @@ class _GemmTimer:
     def summary(self):
         torch.cuda.synchronize()
         by = {1: [0.0, 0.0, 0], 2: [0.0, 0.0, 0]}
-        for e0, e1, flops, impl in self.records:
+        shapes = {}
+        for e0, e1, flops, impl, tag in self.records:
             b = by.get(impl, by[1])
-            b[0] += e0.elapsed_time(e1)
+            ms = e0.elapsed_time(e1)
+            b[0] += ms
             b[1] += flops
             b[2] += 1
+            if tag is not None and impl == 2:
+                t = shapes.setdefault(tag, [0.0, 0.0, 0])
+                t[0] += ms
+                t[1] += flops
+                t[2] += 1
         prep_ms = sum(e0.elapsed_time(e1) for e0, e1 in self.prep)
         tensor = by[2][1] > by[1][1]
         ms, flops, n = by[2] if tensor else by[1]
+        dominant = None
+        if shapes:
+            tag, (tms, tfl, tn) = max(shapes.items(), key=lambda kv: kv[1][0])
+            dominant = dict(product=tag[0], M=tag[1], N=tag[2], K=tag[3], launches=tn, ms_per_launch=tms / tn, flops_per_launch=tfl / tn)
         return dict(kernel='gemm_tcgen05_3xfp16' if tensor else 'gemm_simt_kernel', ms=ms, flops=flops, launches=n, tensor=tensor,
-                    prep_ms=prep_ms, prep_launches=len(self.prep),
+                    prep_ms=prep_ms, prep_launches=len(self.prep), dominant=dominant,
                     other_ms=(by[1] if tensor else by[2])[0], other_flops=(by[1] if tensor else by[2])[1])
 
 
@@ -165,7 +176,8 @@ def linear_fwd_h(xh: H16, wh: H16, b, inv_sigma, act, out=None, out_amax=None):
     y, ldy = _mat(out)
     assert y.data_ptr() == out.data_ptr()
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_fwd_h', ptr(xh.buf), xh.ld, ptr(xh.amax), ptr(wh.buf), wh.ld,
-                                                 ptr(wh.amax), ptr(b), ptr(inv_sigma), ptr(y), ldy, M, N, K, act, ptr(out_amax)), impl=2)
+                                                 ptr(wh.amax), ptr(b), ptr(inv_sigma), ptr(y), ldy, M, N, K, act, ptr(out_amax)), impl=2,
+                   tag=('forward', M, N, K))
     return out
 
 
@@ -182,7 +194,7 @@ def linear_bwd_data_h(dzh: H16, wh: H16, inv_sigma, relu_src, out=None, accumula
         rs, ldr = _mat(relu_src)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_data_h', ptr(dzh.buf), dzh.ld, ptr(dzh.amax), ptr(wh.buf), wh.ld,
                                                  ptr(wh.amax), ptr(inv_sigma), ptr(rs), ldr, ptr(o), ldo, M, N, K,
-                                                 1 if accumulate else 0, ptr(out_amax)), impl=2)
+                                                 1 if accumulate else 0, ptr(out_amax)), impl=2, tag=('data-grad', M, N, K))
     return out
 
 
@@ -195,7 +207,8 @@ def linear_bwd_weight_h(dzh: H16, xh: H16, inv_sigma, out=None, accumulate=False
     o, ldo = _mat(out)
     assert o.data_ptr() == out.data_ptr() and tuple(o.shape) == (N, K)
     GEMM_TIMER.run(2.0 * M * N * K, lambda: call('gcbf_linear_bwd_weight_h', ptr(dzh.buf), dzh.ld, ptr(dzh.amax), ptr(xh.buf), xh.ld,
-                                                 ptr(xh.amax), ptr(inv_sigma), ptr(o), ldo, M, N, K, 1 if accumulate else 0), impl=2)
+                                                 ptr(xh.amax), ptr(inv_sigma), ptr(o), ldo, M, N, K, 1 if accumulate else 0), impl=2,
+                   tag=('weight-grad', M, N, K))
     return out
 
 
