@@ -203,3 +203,53 @@ def test_full_size_properties_c2():
     hdot, h = res['hdot'], res['h'].reshape(-1)
     brute = ((hdot.unsqueeze(0) + hp['alpha'] * h.unsqueeze(1)) >= 0).float().mean()
     assert abs(brute.item() - float(res['acc_h_dot'])) < 1e-6
+
+
+def test_side_stream_overlap_changes_nothing(monkeypatch):
+    """GCBF.train_step with the actor / re-linked passes on a side stream (default for small batches) against the same
+    step on a single stream: same edges, losses, power-iteration state and post-step weights.  Kernels and operand order are
+    identical; only split-K / colsum atomics may reorder, hence 1e-6 instead of bit equality."""
+    meta = dict(env='DubinsCar', n=64, obs=8, graphs=6, area=4.0, seed=77)
+    outs = []
+    for mode in ('0', '1'):
+        monkeypatch.setenv('GCBF_TWO_STREAMS', mode)
+        sb, env, algo, data = _prepare(meta)
+        for _ in range(2):
+            res = algo.train_step(data)
+        torch.cuda.synchronize()
+        b = algo._bucket
+        u = algo.cbf.state_dict()
+        outs.append(dict(s=res['scalars'].clone(), h=res['h'].clone(), hn=res['h_next_new'].clone(), ei=res['edge_index_new'].clone(),
+                         w=b.flat.clone(), g=b.grad.clone(), uv=[v.clone() for k, v in u.items() if k.endswith(('_u', '_v'))]))
+    a, b = outs
+    assert torch.equal(a['ei'], b['ei'])
+    assert torch.allclose(a['s'], b['s'], rtol=0, atol=1e-6)
+    assert torch.allclose(a['h'], b['h'], rtol=0, atol=1e-6) and torch.allclose(a['hn'], b['hn'], rtol=0, atol=1e-6)
+    for x, y in zip(a['uv'], b['uv']):
+        assert torch.allclose(x, y, rtol=0, atol=1e-6)
+    assert (a['g'] - b['g']).norm() <= 1e-4 * a['g'].norm()
+    assert torch.allclose(a['w'], b['w'], rtol=0, atol=2e-6)
+
+
+def test_full_size_properties_c3_graph_and_masks():
+    """BASELINE config C3 (DubinsCar n=1024, 32 obstacles, B=64) at full size: graph and mask invariants that need no
+    oracle -- targets are agents only, sorted (target, source) without duplicates or self loops, within radius and within
+    graph; an agent within 2R of anything is unsafe and never safe; masks are disjoint."""
+    c = synth.CONFIGS['C3']
+    meta = dict(env=c['env'], n=c['num_agents'], obs=c['num_obs'], graphs=8, area=c['area_size'], seed=c['seed'])
+    sb, env, algo, data = _prepare(meta)
+    ei = data.edge_index
+    N = sb.nodes_per_graph
+    key = ei[1] * (ei.max() + 1) + ei[0]
+    assert (key[1:] > key[:-1]).all() and (ei[0] != ei[1]).all()
+    assert ((ei[1] % N) < sb.num_agents).all() and (ei[0] // N == ei[1] // N).all()
+    st = sb.states.to(DEV)
+    d = (st[ei[0], :2] - st[ei[1], :2]).norm(dim=1)
+    assert d.max() < env._params['comm_radius'] + 1e-6
+    safe, unsafe = env.safe_mask(data), env.unsafe_mask(data)
+    assert not (safe & unsafe).any()
+    R = env._params['car_radius']
+    pos = st[:, :2].reshape(8, N, 2)
+    dist = torch.cdist(pos[:, :sb.num_agents], pos) + torch.eye(N, device=DEV)[:sb.num_agents].unsqueeze(0) * 1e6
+    close = (dist.min(dim=2).values < 2 * R).reshape(-1)
+    assert (unsafe[close]).all() and not (safe[close]).any()
