@@ -25,11 +25,13 @@ class StepArena:
         self.active = False
         self.high_water = 0
         self._views = {}
+        self.epoch = 0            # bumped by begin(): lets per-step pools (ops.amax_slot) notice the rewind
 
     def begin(self, device):
         if self.device != device:
             self.chunks, self.device, self._views = [], device, {}
         self.cur, self.off, self.active = 0, 0, True
+        self.epoch += 1
 
     def end(self):
         self.active = False

@@ -90,6 +90,8 @@ GEMM_TIMER = _GemmTimer()
 
 def _mat(t: torch.Tensor) -> Tuple[torch.Tensor, int]:
     """2-D fp32 row-major view with unit inner stride; returns (tensor_keeping_storage_alive, ld)."""
+    if t.dim() == 2 and t.dtype == torch.float32 and t.is_contiguous():
+        return t, t.shape[1]                     # the common case: a dense arena / parameter matrix
     if t.dim() == 1:
         t = t.unsqueeze(1)
     if t.dtype != torch.float32:
@@ -128,8 +130,20 @@ def use_h(M: int, N: int, K: int) -> bool:
     return M >= 256 and N >= 96 and K >= 96 and M * N * K >= (1 << 24)
 
 
+_AMAX_POOL = {'epoch': -1, 'buf': None, 'next': 0}
+
+
 def amax_slot(device) -> torch.Tensor:
-    return _empty(1, device=device, dtype=torch.int32)
+    """One int32 device word for a tensor's max|x| (float bits).  Inside a train step the words come from one pooled arena
+    allocation (a 1-element view each) instead of ~150 separate allocations."""
+    if not ARENA.active or torch.device(device) != ARENA.device:
+        return torch.empty(1, device=device, dtype=torch.int32)
+    p = _AMAX_POOL
+    if p['epoch'] != ARENA.epoch or p['next'] >= 1024:
+        p['buf'], p['epoch'], p['next'] = _empty(1024, device=device, dtype=torch.int32), ARENA.epoch, 0
+    i = p['next']
+    p['next'] = i + 1
+    return p['buf'][i:i + 1]
 
 
 def split_h(t: torch.Tensor, amax: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
@@ -144,7 +158,7 @@ def split_h(t: torch.Tensor, amax: Optional[torch.Tensor] = None, colsum: Option
     else:
         alloc = torch.empty if persistent else _empty
         buf = alloc(2, rows, ld_h, device=m.device, dtype=torch.float16)
-        own_amax = alloc(1, device=m.device, dtype=torch.int32)
+        own_amax = torch.empty(1, device=m.device, dtype=torch.int32) if persistent else amax_slot(m.device)
 
     def go():
         nonlocal amax

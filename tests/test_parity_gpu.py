@@ -207,28 +207,28 @@ def test_full_size_properties_c2():
 
 def test_side_stream_overlap_changes_nothing(monkeypatch):
     """GCBF.train_step with the actor / re-linked passes on a side stream (default for small batches) against the same
-    step on a single stream: same edges, losses, power-iteration state and post-step weights.  Kernels and operand order are
-    identical; only split-K / colsum atomics may reorder, hence 1e-6 instead of bit equality."""
+    step on a single stream: same edges, losses, outputs, power-iteration state and accumulated gradients.  Kernels and
+    operand order are identical; only split-K / colsum atomics may reorder, hence 1e-6 / 1e-5 instead of bit equality.
+    (One step, before the optimizer: Adam's first update is +-lr for every entry whatever its magnitude, so a rounding-level
+    difference in a near-zero gradient entry flips a weight by 2 lr and a second step would no longer be comparable.)"""
     meta = dict(env='DubinsCar', n=64, obs=8, graphs=6, area=4.0, seed=77)
     outs = []
     for mode in ('0', '1'):
         monkeypatch.setenv('GCBF_TWO_STREAMS', mode)
         sb, env, algo, data = _prepare(meta)
-        for _ in range(2):
-            res = algo.train_step(data)
+        res = algo.train_step(data, apply_optim=False)
         torch.cuda.synchronize()
-        b = algo._bucket
         u = algo.cbf.state_dict()
         outs.append(dict(s=res['scalars'].clone(), h=res['h'].clone(), hn=res['h_next_new'].clone(), ei=res['edge_index_new'].clone(),
-                         w=b.flat.clone(), g=b.grad.clone(), uv=[v.clone() for k, v in u.items() if k.endswith(('_u', '_v'))]))
+                         g=algo._bucket.grad.clone(), uv=[v.clone() for k, v in u.items() if k.endswith(('_u', '_v'))]))
     a, b = outs
     assert torch.equal(a['ei'], b['ei'])
     assert torch.allclose(a['s'], b['s'], rtol=0, atol=1e-6)
     assert torch.allclose(a['h'], b['h'], rtol=0, atol=1e-6) and torch.allclose(a['hn'], b['hn'], rtol=0, atol=1e-6)
+    assert len(a['uv']) > 0
     for x, y in zip(a['uv'], b['uv']):
-        assert torch.allclose(x, y, rtol=0, atol=1e-6)
-    assert (a['g'] - b['g']).norm() <= 1e-4 * a['g'].norm()
-    assert torch.allclose(a['w'], b['w'], rtol=0, atol=2e-6)
+        assert torch.equal(x, y)                       # three power iterations per step, in program order, on either layout
+    assert a['g'].norm() > 0 and (a['g'] - b['g']).norm() <= 1e-5 * a['g'].norm()
 
 
 def test_full_size_properties_c3_graph_and_masks():
