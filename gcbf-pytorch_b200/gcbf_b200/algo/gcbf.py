@@ -137,7 +137,7 @@ class GCBF(Algorithm):
             return None
         st = getattr(self, '_side', None)
         if st is None:
-            st = self._side = torch.cuda.Stream(device=dev)
+            st = self._side = torch.cuda.Stream(device=dev, priority=int(os.environ.get('GCBF_SIDE_PRIORITY', '0')))
         return st
 
     def train_step(self, graphs, apply_optim: bool = True, compute_acc_h_dot: bool = True) -> Dict[str, Tensor]:
