@@ -13,4 +13,4 @@ void set_error(const char* fmt, ...) {
 }  // namespace gcbf
 
 extern "C" const char* gcbf_last_error(void) { return gcbf::g_err; }
-extern "C" int gcbf_abi_version(void) { return 1; }
+extern "C" int gcbf_abi_version(void) { return 2; }   // 2: fp16-companion tensor-core entry points (gcbf_linear_*_h)

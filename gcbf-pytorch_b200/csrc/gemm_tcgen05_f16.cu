@@ -602,7 +602,9 @@ extern "C" int gcbf_split_f16(const float* src, int ld, int rows, int cols, cons
 }
 
 extern "C" int gcbf_linear_h_supported(int M, int N, int K) {
-  return (M >= 256 && N >= 96 && K >= 64 && (long long)M * N * K >= (1ll << 24)) ? 1 : 0;
+  // the rule the host mirror applies per layer (forward, data-grad and weight-grad alike): enough rows to fill 128-row tiles,
+  // both feature dimensions wide enough to be a tile / a contraction, and enough work to amortise the split pass
+  return (M >= 256 && N >= 96 && K >= 96 && (long long)M * N * K >= (1ll << 24)) ? 1 : 0;
 }
 
 // Y[M,N] = act(alpha * X W^T + bias): A = X companion [M][K] (K-major), B = W companion [N][K] (K-major)

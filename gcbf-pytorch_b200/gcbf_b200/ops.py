@@ -127,7 +127,7 @@ def use_h(M: int, N: int, K: int) -> bool:
         return False
     if GEMM_IMPL == 2:
         return True
-    return M >= 256 and N >= 96 and K >= 96 and M * N * K >= (1 << 24)
+    return M >= 256 and N >= 96 and K >= 96 and M * N * K >= (1 << 24)     # == gcbf_linear_h_supported (tested)
 
 
 _AMAX_POOL = {'epoch': -1, 'buf': None, 'next': 0}

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/gcbf_b200.h but not exported'
     assert sorted(_C.EXPORTED_SYMBOLS) == declared, set(_C.EXPORTED_SYMBOLS) ^ set(declared)
-    assert _C.lib().gcbf_abi_version() == 1
+    assert _C.lib().gcbf_abi_version() == 2
 
 
 def test_env_cfg_struct_layout():
@@ -181,3 +181,10 @@ def test_tensor_core_dispatch_rule():
         assert not ops.use_h(24196, 2048, 2048)
     finally:
         ops.GEMM_IMPL = old
+    # the host rule is the library's rule
+    from gcbf_b200 import _C
+    lib = _C.lib()
+    for M in (1, 255, 256, 4531, 24196):
+        for N in (1, 32, 95, 96, 128, 2048):
+            for K in (12, 95, 96, 260, 2048):
+                assert ops.use_h(M, N, K) == bool(lib.gcbf_linear_h_supported(M, N, K)), (M, N, K)
