@@ -442,6 +442,62 @@ __global__ void split_h_kernel(const float* __restrict__ src, int ld, int rows, 
   }
 }
 
+// the same split for the aligned case (cols and pitch multiples of 4, 16-byte aligned source): 4 columns per thread,
+// one 16-byte load and one 8-byte store per plane per row, 4 rows in flight
+__device__ __forceinline__ void split4(const float4 x, float s, uint2& hi, uint2& lo) {
+  const float y0 = x.x * s, y1 = x.y * s, y2 = x.z * s, y3 = x.w * s;
+  const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(__fsub_rn(y0, f01.x), __fsub_rn(y1, f01.y));
+  const __half2 l23 = __floats2half2_rn(__fsub_rn(y2, f23.x), __fsub_rn(y3, f23.y));
+  hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+  lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+}
+
+__global__ void __launch_bounds__(256) split_h4_kernel(const float* __restrict__ src, int ld, int rows, int cols,
+                                                       const uint32_t* __restrict__ amax, __half* __restrict__ dst, int ld_h,
+                                                       float* __restrict__ colsum) {
+  const float s = __uint_as_float(scale_bits_from_amax(__ldg(amax)));
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int r0 = blockIdx.y * SPLIT_ROWS;
+  const size_t plane = (size_t)rows * ld_h;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < cols) {
+    const int r1 = min(rows, r0 + SPLIT_ROWS);
+    for (int r = r0 + threadIdx.y; r < r1; r += 32) {        // 4 rows (8 apart) per iteration
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        x[u] = (r + 8 * u < r1) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(r + 8 * u) * ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + 8 * u < r1) {
+          uint2 hi, lo;
+          split4(x[u], s, hi, lo);
+          __half* d = dst + (size_t)(r + 8 * u) * ld_h + c;
+          *reinterpret_cast<uint2*>(d) = hi;
+          *reinterpret_cast<uint2*>(d + plane) = lo;
+          cs[0] += x[u].x; cs[1] += x[u].y; cs[2] += x[u].z; cs[3] += x[u].w;
+        }
+      }
+    }
+  }
+  if (colsum) {
+    __shared__ float red[8][128];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[threadIdx.y][4 * threadIdx.x + j] = cs[j];
+    __syncthreads();
+    if (threadIdx.y < 4) {                                   // 4 x 32 threads reduce the 128 columns of the block
+      const int col = threadIdx.y * 32 + threadIdx.x;
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += red[y][col];
+      const int gc = blockIdx.x * 128 + col;
+      if (gc < cols) atomicAdd(colsum + gc, t);
+    }
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -594,9 +650,16 @@ extern "C" int gcbf_split_f16(const float* src, int ld, int rows, int cols, cons
   if (colsum && !colsum_accumulate) GCBF_CUDA_OK(cudaMemsetAsync(colsum, 0, (size_t)cols * 4, st));
   if (rows == 0 || cols == 0) return GCBF_OK;
   GCBF_REQUIRE(src, "gcbf_split_f16: null src");
-  dim3 grid(ceil_div(cols, 64), ceil_div(rows, th::SPLIT_ROWS)), block(32, 8);
-  th::split_h_kernel<<<grid, block, 0, st>>>(src, ld, rows, cols, reinterpret_cast<const uint32_t*>(amax_slot),
-                                            reinterpret_cast<__half*>(dst), ld_h, colsum);
+  dim3 block(32, 8);
+  if ((cols & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    dim3 grid(ceil_div(cols, 128), ceil_div(rows, th::SPLIT_ROWS));
+    th::split_h4_kernel<<<grid, block, 0, st>>>(src, ld, rows, cols, reinterpret_cast<const uint32_t*>(amax_slot),
+                                               reinterpret_cast<__half*>(dst), ld_h, colsum);
+  } else {
+    dim3 grid(ceil_div(cols, 64), ceil_div(rows, th::SPLIT_ROWS));
+    th::split_h_kernel<<<grid, block, 0, st>>>(src, ld, rows, cols, reinterpret_cast<const uint32_t*>(amax_slot),
+                                              reinterpret_cast<__half*>(dst), ld_h, colsum);
+  }
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }
