@@ -17,10 +17,12 @@
 // No transposes, no padding copies: TMA zero-fills ragged edges of the exact-size tensor maps.
 //
 // Kernel.  Persistent CTAs (grid = #SMs), warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor 2-D boxes into
-// swizzled shared memory, 4 stages x 48 KB), warp 1 = MMA issuer (one thread; 6 tcgen05.mma M128 N256 K16 per stage;
-// accumulators double-buffered in 512 TMEM columns), warps 2-9 = chunk promotion + epilogue.  The tensor core's fp32
-// accumulator truncates on every MMA (tools/acc_probe.py), so K is consumed in chunks of 256: each chunk accumulates in
-// a fresh TMEM buffer and the epilogue warps add the chunk sums in registers with round-to-nearest.
+// swizzled shared memory), warp 1 = MMA issuer (one thread; 6 tcgen05.mma K16 per 32-wide k-block; accumulators
+// double-buffered in 512 TMEM columns), warps 2-9 = chunk promotion + epilogue (output through shared memory + bulk tensor
+// stores).  256-wide tiles run as CTA pairs (cta_group::2: a 256 x 256 tile per pair, each CTA stages half of B, 6 stages x
+// 32 KB); 128-wide tiles as single CTAs.  The tensor core's fp32 accumulator truncates on every MMA (tools/acc_probe.py), so
+// K is consumed in chunks of 256: each chunk accumulates in a fresh TMEM buffer and the epilogue warps add the chunk sums
+// in registers with round-to-nearest.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>

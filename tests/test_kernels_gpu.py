@@ -536,8 +536,8 @@ def test_cbf_and_actor_forward_backward(env_name, n, obs, B, area):
 
 @pytest.mark.parametrize('impl,tol', [(1, 2e-5), (0, 3e-4)])
 def test_net_backward_exact_given_same_relu_masks(impl, tol):
-    """impl 1 = fp32 SIMT GEMMs (exact to fp32 round-off), impl 0 = tcgen05 3xTF32 where the shape qualifies (the
-    tensor core's fp32 accumulator truncates once per MMA, so a K=2048 dot product carries ~1e-5 relative error).
+    """impl 1 = fp32 SIMT GEMMs (exact to fp32 round-off), impl 0 = tcgen05 3xFP16 where the shape qualifies (22-bit
+    operands; measured 1-2e-6 per GEMM, the tolerance below is the one the 3xTF32 predecessor needed).
     The whole fused backward (head -> gamma -> row scatter -> attention aggregation -> gate -> phi -> edge_attr,
     incl. the spectral-norm sigma term) against torch autograd in fp64 ON THE SAME ReLU MASKS (taken from the
     kernels' saved activations), so rounding-level mask flips cannot blur the comparison: tolerance 1e-5 relative."""
