@@ -173,16 +173,10 @@ def test_linear_tcgen05_3xfp16(M, N, K):
 
 
 def _split_reference(x: torch.Tensor):
-    """numpy-level restatement of gcbf_amax_f32 + gcbf_split_f16: s = 2^(14 - floor(log2(max|x|))), hi = fp16(x*s),
-    lo = fp16(x*s - hi) (both round-to-nearest-even).  Returns (amax_bits, hi, lo, s)."""
-    amax = x.abs().max()
-    bits = amax.view(torch.int32).item()
-    e = (bits >> 23) & 0xff
-    s = 1.0 if e in (0, 255) else 2.0 ** min(max(14 - (e - 127), 2 - 127), 252 - 127)
-    xs = x * s
-    hi = xs.half()
-    lo = (xs - hi.float()).half()
-    return bits, hi, lo, s
+    """(amax_bits, hi, lo, s) from the CPU model of the companion format (oracle/fp16x3_model.py)."""
+    import fp16x3_model as F16
+    hi, lo, s = F16.split(x)
+    return x.abs().max().view(torch.int32).item(), hi, lo, s
 
 
 @pytest.mark.parametrize('rows,cols,scale', [(300, 260, 1.0), (1000, 2048, 3e-7), (257, 129, 1e4), (64, 8, 1.0), (5, 1027, 2.5e-3)])

@@ -124,3 +124,40 @@ def test_pretrained_semantic_known_answer():
     assert coll.sum() > 5 and safe.sum() > 50
     assert (h[coll] < 0).float().mean() > 0.9
     assert (h[safe] >= 0).float().mean() > 0.9
+
+
+def test_fp16x3_model_accuracy():
+    """The arithmetic of the tensor-core layers (three fp16 products of [hi | lo] companions, 256-wide chunk promotion) is
+    as accurate as an fp32 GEMM relative to the tensor scale -- for well-scaled data, for activations / gradients spanning
+    several decades, and independently of the absolute magnitude; rows far below the tensor's max keep their ABSOLUTE accuracy
+    (error <= 2^-39 of the max per element) but lose relative accuracy, which is the documented trade of the per-tensor scale."""
+    import fp16x3_model as F16
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 256, 192, 2048
+    b = torch.randn(N, K, generator=g) / 45
+    cases = {
+        'normal': torch.randn(M, K, generator=g),
+        'relu x 1e-6': torch.randn(M, K, generator=g).relu() * 1e-6,
+        'heavy tail': torch.randn(M, K, generator=g) * torch.exp(3 * torch.randn(M, K, generator=g)),
+        'x 1e12': torch.randn(M, K, generator=g) * 1e12,
+    }
+    for name, a in cases.items():
+        ref = a.double() @ b.double().T
+        scale = ref.abs().max()
+        err16 = ((F16.gemm(a, b).double() - ref).abs().max() / scale).item()
+        err32 = (((a @ b.T).double() - ref).abs().max() / scale).item()
+        assert err16 < 1e-6, (name, err16)
+        assert err16 < 4 * err32 + 2e-7, (name, err16, err32)
+    # rows scaled down to 1e-8 of the largest: absolute error stays at the 2^-39-of-max level, relative error of those rows grows
+    a = torch.randn(M, K, generator=g) * 10 ** (-8 * torch.linspace(0, 1, M).unsqueeze(1))
+    ref = a.double() @ b.double().T
+    err = (F16.gemm(a, b).double() - ref).abs()
+    assert (err.max() / ref.abs().max()).item() < 1e-6
+    small = torch.linspace(0, 1, M) > 0.75                        # rows below 1e-6 of the largest: their lo plane is subnormal
+    per_elem_bound = K * (a.abs().max() * 2.0 ** -39) * b.abs().max()
+    assert err[small].max().item() <= per_elem_bound.item()       # absolute accuracy of the small rows ...
+    assert (err[small] / ref[small].abs().clamp_min(1e-300)).max().item() > 1e-6   # ... which is no longer fp32-relative
+    # the companion reconstructs x to 22 bits (or 2^-39 of the max, whichever is larger)
+    hi, lo, s = F16.split(a)
+    rec = (hi.double() + lo.double()) / s
+    assert ((rec - a.double()).abs() <= a.abs().double() * 2.0 ** -21 + a.abs().max().item() * 2.0 ** -39).all()
