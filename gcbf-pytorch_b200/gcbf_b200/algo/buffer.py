@@ -41,8 +41,11 @@ class Buffer:
         self._data = []
         self.safe_data, self.unsafe_data = [], []
 
-    def sample(self, n: int, m: int = 1, balanced_sampling: bool = False) -> list:
-        """n centre indices, each expanded to a window of length <= m of consecutive graphs, de-duplicated."""
+    def sample_windows(self, n: int, m: int = 1, balanced_sampling: bool = False) -> List[tuple]:
+        """The reference's segment sampling (buffer.py:57-95) as index windows: n centres (np.random.randint, or
+        random.choices over the unsafe then the safe positions when balanced), each expanded to [c - m//2, c + m//2],
+        clipped to the buffer and to the end of the previous window (no graph twice).  Consumes the host RNG streams
+        exactly like the reference, so a seeded run samples the same graphs."""
         assert self.size >= max(n, m)
         if balanced_sampling:
             picks = []
@@ -57,5 +60,12 @@ class Buffer:
         for c in centres:
             lo = max(int(c) - m // 2, hi)
             hi = min(int(c) + m // 2 + 1, self.size)
+            out.append((lo, hi))
+        return out
+
+    def sample(self, n: int, m: int = 1, balanced_sampling: bool = False) -> list:
+        """n centre indices, each expanded to a window of length <= m of consecutive graphs, de-duplicated."""
+        out = []
+        for lo, hi in self.sample_windows(n, m, balanced_sampling):
             out.extend(self._data[lo:hi])
         return out

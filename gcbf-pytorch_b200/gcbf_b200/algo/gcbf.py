@@ -92,6 +92,7 @@ class GCBF(Algorithm):
         self._bucket: Optional[_FlatBucket] = None
         self.buffer = Buffer()
         self.memory = Buffer()
+        self.device_replay = False                         # use_device_replay() swaps the two lists for device rings
         self.batch_size = batch_size
         self.params = params if params is not None else {
             'alpha': 1.0, 'eps': 0.02, 'inner_iter': 10, 'loss_action_coef': 0.001, 'loss_unsafe_coef': 1.,
@@ -114,6 +115,15 @@ class GCBF(Algorithm):
 
     def is_update(self, step: int) -> bool:
         return step % self.batch_size == 0
+
+    def use_device_replay(self, capacity: int = 4096):
+        """Keep visited graphs as device-resident (states, u_ref) rings and collate sampled batches on the GPU
+        (algo/device_buffer.py) instead of Python lists of `Data` + `Batch.from_data_list`.  Same sampling semantics."""
+        from .device_buffer import DeviceReplay
+        assert self.buffer.size == 0 and self.memory.size == 0, 'switch before collecting data'
+        self.buffer, self.memory = DeviceReplay(self.device, capacity), DeviceReplay(self.device, capacity)
+        self.device_replay = True
+        return self
 
     # ---- the train step -----------------------------------------------------------------------------
     def _ensure_bucket(self) -> _FlatBucket:
@@ -259,10 +269,18 @@ class GCBF(Algorithm):
         for i_inner in range(self.params['inner_iter']):
             if self.memory.size == 0:
                 graph_list = self.buffer.sample(self.batch_size // 5, seg_len)
+                parts = [(self.buffer, graph_list)]
             else:
-                graph_list = (self.buffer.sample(self.batch_size // 10, seg_len, True) +
-                              self.memory.sample(self.batch_size // 5 - self.batch_size // 10, seg_len, True))
-            res = self.train_step(Batch.from_data_list(graph_list))
+                from_buffer = self.buffer.sample(self.batch_size // 10, seg_len, True)
+                from_memory = self.memory.sample(self.batch_size // 5 - self.batch_size // 10, seg_len, True)
+                graph_list = from_buffer + from_memory
+                parts = [(self.buffer, from_buffer), (self.memory, from_memory)]
+            if self.device_replay:
+                from .device_buffer import collate
+                batch = collate(self._env, parts)            # gathers on the device rings + ONE batched graph build
+            else:
+                batch = Batch.from_data_list(graph_list)
+            res = self.train_step(batch)
             s = res['scalars'].tolist()                                  # the one host sync per inner iteration
             info = {'acc/safe': s[5], 'acc/unsafe': s[4], 'acc/derivative': float(res['acc_h_dot'])}
             if writer is not None:

@@ -188,3 +188,50 @@ def test_tensor_core_dispatch_rule():
         for N in (1, 32, 95, 96, 128, 2048):
             for K in (12, 95, 96, 260, 2048):
                 assert ops.use_h(M, N, K) == bool(lib.gcbf_linear_h_supported(M, N, K)), (M, N, K)
+
+
+def test_device_replay_matches_list_buffer(monkeypatch):
+    """The device-resident replay ring (algo/device_buffer.py) against the list buffer that mirrors the reference's
+    gcbf/algo/buffer.py: identical safe / unsafe bookkeeping, drop-oldest, merge and -- under the same host RNG seeds -- the
+    same sampled graphs, through capacity growth and ring wrap-around (CPU tensors: the ring is plain torch indexing)."""
+    import random
+    import types
+    import numpy as np
+    import torch
+    from gcbf_b200.algo.buffer import Buffer
+    from gcbf_b200.algo.device_buffer import DeviceReplay
+    monkeypatch.setattr(Buffer, 'MAX_SIZE', 37)
+
+    def graph(i):
+        return types.SimpleNamespace(states=torch.full((5, 4), float(i)), u_ref=torch.full((3, 2), -float(i)), tag=i)
+
+    def check(lst, ring):
+        assert lst.size == ring.size and lst.safe_data == ring.safe_data and lst.unsafe_data == ring.unsafe_data
+        want = torch.stack([g.states for g in lst.data]) if lst.size else torch.empty(0, 5, 4)
+        assert torch.equal(ring.states_of(range(ring.size)), want)
+        for seed, (n, m, bal) in enumerate([(6, 3, False), (8, 3, True), (4, 1, False), (10, 5, True)]):
+            if lst.size < max(n, m):
+                continue
+            np.random.seed(seed), random.seed(seed)
+            a = [g.tag for g in lst.sample(n, m, bal)]
+            np.random.seed(seed), random.seed(seed)
+            idx = ring.sample(n, m, bal)
+            assert [int(x) for x in ring.states_of(idx)[:, 0, 0]] == a and [int(-x) for x in ring.u_ref_of(idx)[:, 0, 0]] == a
+
+    lst, ring = Buffer(), DeviceReplay('cpu', capacity=8)
+    for i in range(60):                                   # grows 8 -> 16 -> 32 -> 37, then wraps (drop-oldest)
+        lst.append(graph(i), is_safe=(i % 3 != 0))
+        ring.append(graph(i), is_safe=(i % 3 != 0))
+        if i % 7 == 0:
+            check(lst, ring)
+    check(lst, ring)
+    lst2, ring2 = Buffer(), DeviceReplay('cpu', capacity=4)
+    for i in range(100, 125):
+        lst2.append(graph(i), is_safe=(i % 2 == 0))
+        ring2.append(graph(i), is_safe=(i % 2 == 0))
+    lst.merge(lst2), ring.merge(ring2)                    # 37 + 25 > MAX_SIZE: the oldest 25 drop out
+    check(lst, ring)
+    lst.clear(), ring.clear()
+    check(lst, ring)
+    lst.merge(lst2), ring.merge(ring2)
+    check(lst, ring)

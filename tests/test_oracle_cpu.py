@@ -161,3 +161,66 @@ def test_fp16x3_model_accuracy():
     hi, lo, s = F16.split(a)
     rec = (hi.double() + lo.double()) / s
     assert ((rec - a.double()).abs() <= a.abs().double() * 2.0 ** -21 + a.abs().max().item() * 2.0 ** -39).all()
+
+
+@pytest.mark.skipif(not has_ref, reason='reference checkout not present (GPU box)')
+def test_buffer_sampling_matches_live_reference(tmp_path):
+    """The replay buffers' index semantics (append, safe / unsafe bookkeeping, merge, segment sampling and its consumption
+    of the host RNG streams) against the reference's OWN gcbf/algo/buffer.py, run in a subprocess on the shim."""
+    script = tmp_path / 'run_ref_buffer.py'
+    script.write_text(f"""
+import sys, json, random
+import numpy as np
+sys.path.insert(0, {os.path.join(ROOT, 'oracle')!r})
+import ref_loader
+ref_loader.load_reference()
+from gcbf.algo.buffer import Buffer
+buf, other = Buffer(), Buffer()
+for i in range(90):
+    buf.append(i, i % 4 != 0)
+for i in range(200, 230):
+    other.append(i, i % 3 == 0)
+out = []
+for seed, (n, m, bal) in enumerate([(12, 3, False), (16, 3, True), (7, 1, False), (20, 5, True)]):
+    np.random.seed(seed); random.seed(seed)
+    out.append(buf.sample(n, m, bal))
+buf.merge(other)
+np.random.seed(9); random.seed(9)
+out.append(buf.sample(24, 3, True))
+out.append([buf.size, buf.safe_data[-3:], buf.unsafe_data[-3:]])
+json.dump(out, open({str(tmp_path / 'out.json')!r}, 'w'))
+""")
+    subprocess.check_call([sys.executable, str(script)], stderr=subprocess.DEVNULL)
+    import json
+    import random
+    import types
+    import numpy as np
+    want = json.load(open(tmp_path / 'out.json'))
+    from gcbf_b200.algo.buffer import Buffer
+    from gcbf_b200.algo.device_buffer import DeviceReplay
+
+    def graph(i):
+        return types.SimpleNamespace(states=torch.full((2, 4), float(i)), u_ref=torch.full((2, 2), float(i)))
+
+    buf, other, ring, ring_other = Buffer(), Buffer(), DeviceReplay('cpu', 16), DeviceReplay('cpu', 16)
+    for i in range(90):
+        buf.append(i, i % 4 != 0)
+        ring.append(graph(i), i % 4 != 0)
+    for i in range(200, 230):
+        other.append(i, i % 3 == 0)
+        ring_other.append(graph(i), i % 3 == 0)
+    got, got_ring = [], []
+    for seed, (n, m, bal) in enumerate([(12, 3, False), (16, 3, True), (7, 1, False), (20, 5, True)]):
+        np.random.seed(seed), random.seed(seed)
+        got.append(buf.sample(n, m, bal))
+        np.random.seed(seed), random.seed(seed)
+        got_ring.append([int(x) for x in ring.states_of(ring.sample(n, m, bal))[:, 0, 0]])
+    buf.merge(other), ring.merge(ring_other)
+    np.random.seed(9), random.seed(9)
+    got.append(buf.sample(24, 3, True))
+    np.random.seed(9), random.seed(9)
+    got_ring.append([int(x) for x in ring.states_of(ring.sample(24, 3, True))[:, 0, 0]])
+    got.append([buf.size, buf.safe_data[-3:], buf.unsafe_data[-3:]])
+    assert got == want
+    assert got_ring == want[:-1]
+    assert [ring.size, ring.safe_data[-3:], ring.unsafe_data[-3:]] == want[-1]

@@ -253,3 +253,46 @@ def test_full_size_properties_c3_graph_and_masks():
     dist = torch.cdist(pos[:, :sb.num_agents], pos) + torch.eye(N, device=DEV)[:sb.num_agents].unsqueeze(0) * 1e6
     close = (dist.min(dim=2).values < 2 * R).reshape(-1)
     assert (unsafe[close]).all() and not (safe[close]).any()
+
+
+@pytest.mark.parametrize('env_name,n,obs,area', [('SimpleCar', 12, 0, 2.0), ('DubinsCar', 10, 4, 2.0), ('SimpleDrone', 6, 6, 1.0)])
+def test_device_replay_collates_like_from_data_list(env_name, n, obs, area):
+    """SURVEY 8f-2 (replay half): a batch gathered from the device-resident ring and re-linked by the batched graph kernels
+    is the batch `Batch.from_data_list` builds from the stored `Data` objects -- same edges (bit-exact), edge features,
+    node types, states and nominal controls -- and GCBF.update runs on it."""
+    import random
+    import numpy as np
+    from gcbf_b200.algo.device_buffer import collate
+    from gcbf_b200.data import Batch
+    meta = dict(env=env_name, n=n, obs=obs, graphs=1, area=area, seed=61)
+    sb, env, algo, data = _prepare(meta)
+    _, _, algo_ring, _ = _prepare(meta)
+    algo_ring._env = env
+    algo_ring.use_device_replay(capacity=4)
+    for k in range(14):
+        sbk = synth.make_states(env_name, n, obs, 1, area, 300 + k)
+        g = env.graph_from_states(sbk.states.to(DEV))
+        algo.buffer.append(g, is_safe=(k % 3 != 0))
+        algo_ring.buffer.append(g, is_safe=(k % 3 != 0))
+    for seed, (cnt, m, bal) in enumerate([(5, 3, False), (6, 3, True)]):
+        np.random.seed(seed), random.seed(seed)
+        want = Batch.from_data_list(algo.buffer.sample(cnt, m, bal))
+        np.random.seed(seed), random.seed(seed)
+        got = collate(env, [(algo_ring.buffer, algo_ring.buffer.sample(cnt, m, bal))])
+        assert torch.equal(got.edge_index, want.edge_index)
+        for key in ('states', 'u_ref', 'edge_attr', 'x'):
+            assert torch.equal(getattr(got, key), getattr(want, key)), key
+        if hasattr(want, 'agent_mask'):
+            assert torch.equal(got.agent_mask, want.agent_mask)
+    algo_ring.batch_size = 20
+    algo_ring.params['inner_iter'] = 2
+    np.random.seed(3), random.seed(3)
+    info = algo_ring.update(1, None)
+    assert set(info) == {'acc/safe', 'acc/unsafe', 'acc/derivative'} and all(v == v for v in info.values())
+    assert algo_ring.buffer.size == 0 and algo_ring.memory.size == 14
+    np.random.seed(4), random.seed(4)
+    for k in range(6):
+        sbk = synth.make_states(env_name, n, obs, 1, area, 400 + k)
+        algo_ring.buffer.append(env.graph_from_states(sbk.states.to(DEV)), is_safe=(k % 2 == 0))
+    info = algo_ring.update(2, None)                           # balanced sampling from the fresh buffer and the merged memory
+    assert all(v == v for v in info.values()) and algo_ring.memory.size == 20
