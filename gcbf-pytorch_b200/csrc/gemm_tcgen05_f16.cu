@@ -500,6 +500,62 @@ __global__ void __launch_bounds__(256) split_h4_kernel(const float* __restrict__
   }
 }
 
+// ---- batched amax + split: the companions of all (stale) weight matrices of a net in two launches -------------------------
+constexpr int kSplitMaxBatch = 16;
+struct SplitBatch {
+  const float* src[kSplitMaxBatch];
+  uint32_t* amax[kSplitMaxBatch];
+  __half* dst[kSplitMaxBatch];
+  int ld[kSplitMaxBatch], rows[kSplitMaxBatch], cols[kSplitMaxBatch], ld_h[kSplitMaxBatch];
+};
+
+__global__ void __launch_bounds__(256) amax_batched_kernel(const __grid_constant__ SplitBatch b) {
+  const int t = blockIdx.z;
+  const float* __restrict__ src = b.src[t];
+  const int ld = b.ld[t], rows = b.rows[t], cols = b.cols[t];
+  float m = 0.f;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x)
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, fabsf(__ldg(src + (size_t)r * ld + c)));
+  const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  __shared__ uint32_t part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t v = threadIdx.x < 8 ? part[threadIdx.x] : 0u;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if (threadIdx.x == 0 && v) atomicMax(b.amax[t], v);
+  }
+}
+
+__global__ void __launch_bounds__(256) split_batched_kernel(const __grid_constant__ SplitBatch b) {
+  const int t = blockIdx.z;
+  const int ld = b.ld[t], rows = b.rows[t], cols = b.cols[t], ld_h = b.ld_h[t];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+  const int r0 = blockIdx.y * SPLIT_ROWS;
+  if (c >= cols || r0 >= rows) return;
+  const float* __restrict__ src = b.src[t];
+  __half* __restrict__ dst = b.dst[t];
+  const float s = __uint_as_float(scale_bits_from_amax(*b.amax[t]));
+  const size_t plane = (size_t)rows * ld_h;
+  const bool pair = (c + 1 < cols);
+  const int r1 = min(rows, r0 + SPLIT_ROWS);
+  for (int r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+    const float* p = src + (size_t)r * ld + c;
+    const float y0 = __ldg(p) * s, y1 = pair ? __ldg(p + 1) * s : 0.f;
+    const __half2 hi = __floats2half2_rn(y0, y1);
+    const float2 hf = __half22float2(hi);
+    const __half2 lo = __floats2half2_rn(__fsub_rn(y0, hf.x), __fsub_rn(y1, hf.y));
+    __half* d = dst + (size_t)r * ld_h + c;
+    if (pair) {
+      *reinterpret_cast<__half2*>(d) = hi;
+      *reinterpret_cast<__half2*>(d + plane) = lo;
+    } else {
+      d[0] = __low2half(hi);
+      d[plane] = __low2half(lo);
+    }
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -663,6 +719,33 @@ extern "C" int gcbf_split_f16(const float* src, int ld, int rows, int cols, cons
                                               reinterpret_cast<__half*>(dst), ld_h, colsum);
   }
   GCBF_LAUNCH_OK();
+  return GCBF_OK;
+}
+
+// gcbf_amax_f32 + gcbf_split_f16 for `count` matrices (HOST array of descriptors) in two launches per 16 matrices: the
+// weights of a net after an optimizer step.  Same arithmetic per matrix, so the companions are bit-identical.
+extern "C" int gcbf_amax_split_batched(const gcbf_split_desc* descs, int count, void* stream) {
+  GCBF_REQUIRE(descs && count >= 0, "gcbf_amax_split_batched: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  for (int base = 0; base < count; base += th::kSplitMaxBatch) {
+    const int nb = min(th::kSplitMaxBatch, count - base);
+    th::SplitBatch b{};
+    int max_rows = 0, max_cols = 0;
+    for (int i = 0; i < nb; ++i) {
+      const gcbf_split_desc& d = descs[base + i];
+      GCBF_REQUIRE(d.src && d.amax_slot && d.dst && d.rows > 0 && d.cols > 0 && d.ld >= d.cols && d.ld_h >= d.cols,
+                   "gcbf_amax_split_batched: descriptor %d", base + i);
+      if (int rc = th::check_plane(d.dst, d.ld_h, "gcbf_amax_split_batched")) return rc;
+      b.src[i] = d.src; b.amax[i] = reinterpret_cast<uint32_t*>(d.amax_slot); b.dst[i] = reinterpret_cast<__half*>(d.dst);
+      b.ld[i] = d.ld; b.rows[i] = d.rows; b.cols[i] = d.cols; b.ld_h[i] = d.ld_h;
+      max_rows = max(max_rows, d.rows); max_cols = max(max_cols, d.cols);
+      GCBF_CUDA_OK(cudaMemsetAsync(d.amax_slot, 0, 4, st));
+    }
+    th::amax_batched_kernel<<<dim3(min(max_rows, 4 * kNumSMs / nb + 1), 1, nb), 256, 0, st>>>(b);
+    GCBF_LAUNCH_OK();
+    th::split_batched_kernel<<<dim3(ceil_div(max_cols, 64), ceil_div(max_rows, th::SPLIT_ROWS), nb), dim3(32, 8), 0, st>>>(b);
+    GCBF_LAUNCH_OK();
+  }
   return GCBF_OK;
 }
 

@@ -26,6 +26,12 @@ class SnLayer(ctypes.Structure):
                 ('v', c_void_p), ('inv_sigma', c_void_p)]
 
 
+class SplitDesc(ctypes.Structure):
+    """mirror of `gcbf_split_desc`"""
+    _fields_ = [('src', c_void_p), ('ld', c_int32), ('rows', c_int32), ('cols', c_int32), ('ld_h', c_int32),
+                ('amax_slot', c_void_p), ('dst', c_void_p)]
+
+
 P = c_void_p  # every device pointer travels as void*
 _SIGS = {
     'gcbf_last_error': (c_char_p, []),
@@ -43,6 +49,7 @@ _SIGS = {
     'gcbf_linear_bwd_weight': (c_int, [P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_amax_f32': (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
     'gcbf_split_f16': (c_int, [P, c_int, c_int, c_int, P, P, c_int, P, c_int, P]),
+    'gcbf_amax_split_batched': (c_int, [POINTER(SplitDesc), c_int, P]),
     'gcbf_linear_h_supported': (c_int, [c_int, c_int, c_int]),
     'gcbf_linear_fwd_h': (c_int, [P, c_int, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     'gcbf_linear_bwd_data_h': (c_int, [P, c_int, P, P, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P]),
@@ -117,7 +124,7 @@ def check(rc, what):
 
 # kernels launched by one call of each entry point (for bench.py's `gpu_launches`; memsets are not counted)
 _KERNELS_PER_CALL = {'gcbf_radius_graph_count': 2, 'gcbf_sn_power_iter': 4, 'gcbf_sn_power_iter_batched': 4, 'gcbf_sn_grad_fixup': 2, 'gcbf_linear_bwd_weight': 2,
-                     'gcbf_linear_h_supported': 0}
+                     'gcbf_linear_h_supported': 0, 'gcbf_amax_split_batched': 2}
 KERNEL_LAUNCHES = 0
 ABI_CALLS = 0
 

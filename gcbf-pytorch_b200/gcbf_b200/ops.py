@@ -182,6 +182,43 @@ def weight_h(W: torch.Tensor) -> H16:
     return h
 
 
+def prepare_weights(jobs) -> None:
+    """Refresh the stale companions of several weight matrices in two launches (instead of a memset + amax + split each).
+    `jobs`: iterable of (LinearSpec, M) -- the layers about to run with M rows; layers that do not qualify for the tensor
+    core or whose companion is current are skipped.  Bit-identical to weight_h() layer by layer."""
+    stale = []
+    for L, M in jobs:
+        W = L.W
+        N, K = W.shape
+        if not use_h(M, N, K):
+            continue
+        stamp = (WEIGHT_EPOCH, W._version, W.data_ptr(), tuple(W.shape))
+        ent = getattr(W, '_gcbf_h16', None)
+        if ent is not None and ent[0] == stamp:
+            continue
+        if any(W is w for w, _, _ in stale):
+            continue
+        if ent is not None and ent[1].rows == N and ent[1].cols == K:
+            h = ent[1]
+        else:
+            ld_h = (K + 7) // 8 * 8
+            h = H16(torch.empty(2, N, ld_h, device=W.device, dtype=torch.float16),
+                    torch.empty(1, device=W.device, dtype=torch.int32), N, K, ld_h)
+        stale.append((W, stamp, h))
+    if not stale:
+        return
+    arr = (_C.SplitDesc * len(stale))()
+    keep = []
+    for i, (W, _, h) in enumerate(stale):
+        Wm, ldw = _mat(W.detach())
+        keep.append(Wm)
+        a = arr[i]
+        a.src, a.ld, a.rows, a.cols, a.ld_h, a.amax_slot, a.dst = ptr(Wm), ldw, h.rows, h.cols, h.ld, ptr(h.amax), ptr(h.buf)
+    GEMM_TIMER.run_prep(lambda: call('gcbf_amax_split_batched', arr, len(stale)))
+    for W, stamp, h in stale:
+        W._gcbf_h16 = (stamp, h)
+
+
 def linear_fwd_h(xh: H16, wh: H16, b, inv_sigma, act, out=None, out_amax=None):
     M, K, N = xh.rows, xh.cols, wh.rows
     assert wh.cols == K, (M, K, wh.rows, wh.cols)
@@ -678,6 +715,8 @@ def net_forward(spec: NetSpec, x, edge_attr, edge_index, rowptr, row_index, head
     # the power iterations depend on the weights only: all spectral-normalised layers of the net in one batched call
     n_phi, n_gate, n_gamma = len(spec.phi), len(spec.gate), len(spec.gamma)
     isg, uvs = sn_power_iter_batched(spec.all_layers(), snapshot=save)
+    R = row_index.numel() if row_index is not None else Nn
+    prepare_weights([(L, E) for L in spec.phi + spec.gate] + [(L, R) for L in spec.gamma + (spec.head or [])])
     isg_phi, isg_gate = isg[:n_phi], isg[n_phi:n_phi + n_gate]
     isg_gamma, isg_head = isg[n_phi + n_gate:n_phi + n_gate + n_gamma], isg[n_phi + n_gate + n_gamma:]
     uv_phi, uv_gate = uvs[:n_phi], uvs[n_phi:n_phi + n_gate]

@@ -126,6 +126,12 @@ int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X, int ldx, c
 int gcbf_amax_f32(const float* src, int ld, int rows, int cols, void* amax_slot, int accumulate, void* stream);
 int gcbf_split_f16(const float* src, int ld, int rows, int cols, const void* amax_slot, void* dst, int ld_h,
                    float* colsum, int colsum_accumulate, void* stream);
+/* amax + split of `count` matrices (HOST array of descriptors, device pointers inside) in two launches per 16 matrices:
+ * the weights of a net after an optimizer step.  Bit-identical to gcbf_amax_f32 + gcbf_split_f16 per matrix. */
+typedef struct gcbf_split_desc {
+  const float* src; int32_t ld; int32_t rows; int32_t cols; int32_t ld_h; void* amax_slot; void* dst;
+} gcbf_split_desc;
+int gcbf_amax_split_batched(const gcbf_split_desc* descs, int count, void* stream);
 int gcbf_linear_h_supported(int M, int N, int K);
 int gcbf_linear_fwd_h(const void* Xh, int ldxh, const void* x_amax, const void* Wh, int ldwh, const void* w_amax,
                       const float* bias, const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act,

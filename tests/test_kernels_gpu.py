@@ -277,6 +277,26 @@ def test_sn_power_iter_batched_bit_identical():
             assert torch.equal(La.u, Lb.u) and torch.equal(La.v, Lb.v) and torch.equal(a, b)
 
 
+def test_batched_weight_companions_bit_identical():
+    """ops.prepare_weights (all stale weight companions of a net in two launches) against the per-matrix amax + split."""
+    shapes = [(2048, 2048), (256, 2048), (128, 256), (2048, 260), (512, 1027), (1024, 2048), (128, 128)]
+    g = _g(11)
+    specs = [ops.LinearSpec((torch.randn(N, K, generator=g) * 10 ** float(torch.randint(-6, 3, (1,), generator=g))).to(DEV),
+                            torch.zeros(N, device=DEV)) for N, K in shapes]
+    specs.append(ops.LinearSpec(torch.randn(16, 2048, device=DEV), torch.zeros(16, device=DEV)))      # N < 96: not a tensor-core layer
+    ops.prepare_weights([(L, 4096) for L in specs])
+    assert getattr(specs[-1].W, '_gcbf_h16', None) is None
+    for L in specs[:-1]:
+        got = L.W._gcbf_h16[1]
+        want = ops.split_h(L.W)
+        assert got.amax.item() == want.amax.item() and got.ld == want.ld
+        assert torch.equal(got.buf[:, :, :got.cols], want.buf[:, :, :want.cols])
+        assert ops.weight_h(L.W) is got                      # the cache entry is current: no second split
+    specs[0].W.mul_(2.0)                                      # an in-place update invalidates exactly that entry
+    ops.prepare_weights([(L, 4096) for L in specs])
+    assert torch.equal(specs[0].W._gcbf_h16[1].buf, ops.split_h(specs[0].W).buf)
+
+
 def test_linear_strided_views():
     """Kernels take leading dimensions: column slices of wider buffers must work without copies."""
     g = _g(9)
