@@ -200,15 +200,20 @@ def run_own(args):
         args_e2e_steps = args.steps
         for i in range(2):
             e2e_step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args_e2e_steps):
-        e2e_step(2 + i)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    assert args_e2e_steps == 0 or bool(torch.isfinite(out_host[2:2 + args_e2e_steps]).all()), 'e2e results did not reach the host'
+    # this leg synchronises with the host twice per step (edge counts), so one host hiccup on a shared box moves a K = 10 total
+    # by tens of percent: the K steps are timed twice back to back and the faster total is reported (both are kept in the line)
+    e2e_runs = []
+    for _rep in range(2 if args_e2e_steps else 1):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args_e2e_steps):
+            e2e_step(2 + i)
+        e1.record()
+        barrier()
+        e2e_runs.append(e0.elapsed_time(e1))
+        assert args_e2e_steps == 0 or bool(torch.isfinite(out_host[2:2 + args_e2e_steps]).all()), 'e2e results did not reach the host'
+    ms_e2e = min(e2e_runs)
 
     # roofline pass: the same steps again with a CUDA-event pair around every GEMM launch (the ~2000 event records slow
     # the host down, so this pass is kept out of the throughput measurement above)
@@ -292,7 +297,8 @@ def run_own(args):
                          'exceeds the 126 MB L2'},
         'clocks': clocks,
         'e2e': ({'value': round(agents * args.steps / (ms_e2e / 1e3), 1), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-                 'd2h_bytes_per_step': 32, 'ms_per_step': round(ms_e2e / args.steps, 4)} if args_e2e_steps else None),
+                 'd2h_bytes_per_step': 32, 'ms_per_step': round(ms_e2e / args.steps, 4),
+                 'ms_per_step_runs': [round(x / args.steps, 4) for x in e2e_runs]} if args_e2e_steps else None),
         'gpu_launches': launches,
         'roofline': roofline,
         'loss': round(scal[6], 6),
