@@ -510,15 +510,28 @@ struct SplitBatch {
 };
 
 __global__ void __launch_bounds__(256) amax_batched_kernel(const __grid_constant__ SplitBatch b) {
+  // one warp per row (8 rows per block), 16-byte loads where the matrix allows them; blocks beyond a matrix's rows exit
   const int t = blockIdx.z;
-  const float* __restrict__ src = b.src[t];
   const int ld = b.ld[t], rows = b.rows[t], cols = b.cols[t];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* __restrict__ src = b.src[t];
+  const bool vec = ((cols & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
   float m = 0.f;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x)
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, fabsf(__ldg(src + (size_t)r * ld + c)));
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const float* row = src + (size_t)r * ld;
+    if (vec) {
+      const float4* p = reinterpret_cast<const float4*>(row);
+      for (int c = lane; c < (cols >> 2); c += 32) {
+        const float4 x = __ldg(p + c);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y))), fmaxf(fabsf(x.z), fabsf(x.w)));
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) m = fmaxf(m, fabsf(__ldg(row + c)));
+    }
+  }
   const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
   __shared__ uint32_t part[8];
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
+  if (lane == 0) part[warp] = w;
   __syncthreads();
   if (threadIdx.x < 32) {
     uint32_t v = threadIdx.x < 8 ? part[threadIdx.x] : 0u;
@@ -741,7 +754,7 @@ extern "C" int gcbf_amax_split_batched(const gcbf_split_desc* descs, int count, 
       max_rows = max(max_rows, d.rows); max_cols = max(max_cols, d.cols);
       GCBF_CUDA_OK(cudaMemsetAsync(d.amax_slot, 0, 4, st));
     }
-    th::amax_batched_kernel<<<dim3(min(max_rows, 4 * kNumSMs / nb + 1), 1, nb), 256, 0, st>>>(b);
+    th::amax_batched_kernel<<<dim3(min(ceil_div(max_rows, 8), 8 * kNumSMs), 1, nb), 256, 0, st>>>(b);
     GCBF_LAUNCH_OK();
     th::split_batched_kernel<<<dim3(ceil_div(max_cols, 64), ceil_div(max_rows, th::SPLIT_ROWS), nb), dim3(32, 8), 0, st>>>(b);
     GCBF_LAUNCH_OK();
