@@ -1,8 +1,15 @@
-"""Trainer with the interface of reference gcbf/trainer/trainer.py:15-141 (host loop; the arithmetic it drives --
-actor forward, env.step, algo.update -- is the kernel path).  TensorBoard is optional."""
+"""Outer training loop with the call surface of the reference's `gcbf.trainer.Trainer` (gcbf/trainer/trainer.py:15-141):
+`Trainer(env, env_test, algo, log_dir).train(steps, eval_interval, eval_epi)` and `.eval(step, eval_epi)`.
+
+The loop itself is host glue; what it drives -- the actor forward inside `algo.step`, `env.step`, `algo.update`, and
+`algo.apply` during evaluation -- is the kernel path.  Behaviour kept from the reference: the exploration probability decays
+linearly from 1 to 0 over the run, u_ref is attached to a graph before the algorithm sees it, checkpoints go to
+`<log_dir>/models/step_<k>`, the evaluation episodes use the test-time controller and report the mean episode reward, the
+fraction of agents that never collided and the fraction that reached their goal.  TensorBoard is optional (scalars are dropped
+when it is not installed); progress lines go to stdout."""
 import os
-from time import time
-from typing import Tuple
+import time
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -10,65 +17,97 @@ import torch
 from ..data import Data
 
 
-class _NullWriter:
-    def add_scalar(self, *a, **k):
-        pass
+class _DropScalars:
+    def add_scalar(self, *args, **kwargs):
+        return None
+
+
+def _make_writer(path: str):
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+        return SummaryWriter(log_dir=path)
+    except Exception:
+        return _DropScalars()
 
 
 class Trainer:
 
     def __init__(self, env, env_test, algo, log_dir: str):
-        self.env, self.env_test, self.algo, self.log_dir = env, env_test, algo, log_dir
+        self.env, self.env_test, self.algo = env, env_test, algo
+        self.log_dir = log_dir
         self.model_dir = os.path.join(log_dir, 'models')
         os.makedirs(self.model_dir, exist_ok=True)
-        try:
-            from torch.utils.tensorboard import SummaryWriter
-            self.writer = SummaryWriter(log_dir=os.path.join(log_dir, 'summary'))
-        except Exception:   # tensorboard missing: keep training
-            self.writer = _NullWriter()
+        self.writer = _make_writer(os.path.join(log_dir, 'summary'))
 
+    # ---- rollout --------------------------------------------------------------------------------------------
+    @staticmethod
+    def _with_u_ref(env, graph):
+        graph.update(Data(u_ref=env.u_ref(graph)))
+        return graph
+
+    def _rollout_step(self, graph, explore_prob: float):
+        """One environment transition of the training env; returns the graph the next transition starts from."""
+        env, algo = self.env, self.algo
+        self._with_u_ref(env, graph)
+        action = algo.step(graph, prob=explore_prob)
+        nxt, reward, done, _ = env.step(action)
+        self._with_u_ref(env, nxt)
+        algo.post_step(graph, action, reward, done, nxt)
+        return env.reset() if done else nxt
+
+    # ---- training -------------------------------------------------------------------------------------------
     def train(self, steps: int, eval_interval: int, eval_epi: int):
-        start = time()
-        data = self.env.reset()
-        verbose = None
-        for step in range(1, steps + 1):
-            data.update(Data(u_ref=self.env.u_ref(data)))
-            action = self.algo.step(data, prob=1 - (step - 1) / steps)
-            next_data, reward, done, info = self.env.step(action)
-            next_data.update(Data(u_ref=self.env.u_ref(next_data)))
-            self.algo.post_step(data, action, reward, done, next_data)
-            data = self.env.reset() if done else next_data
+        t0 = time.time()
+        graph = self.env.reset()
+        last_update: Optional[Dict[str, float]] = None
+        for k in range(steps):
+            step = k + 1
+            graph = self._rollout_step(graph, explore_prob=1.0 - k / steps)
             if self.algo.is_update(step):
-                verbose = self.algo.update(step, self.writer)
+                last_update = self.algo.update(step, self.writer)
             if eval_interval > 0 and step % eval_interval == 0:
-                if eval_epi > 0:
-                    reward, eval_info = self.eval(step, eval_epi)
-                    print(f'step: {step}, time: {time() - start:.0f}s, reward: {reward:.2f}, ' +
-                          ', '.join(f'{k}: {v}' for k, v in eval_info.items()))
-                if verbose is not None:
-                    print(f'step: {step}, ' + ', '.join(f'{k}: {v:.3f}' for k, v in verbose.items()))
-                self.algo.save(os.path.join(self.model_dir, f'step_{step}'))
-                self.algo._env = self.env
-        print(f'> Done in {time() - start:.0f} seconds')
+                self._checkpoint_and_report(step, eval_epi, last_update, time.time() - t0)
+        print(f'> Done in {time.time() - t0:.0f} seconds')
+
+    def _checkpoint_and_report(self, step: int, eval_epi: int, last_update, elapsed: float):
+        if eval_epi > 0:
+            reward, info = self.eval(step, eval_epi)
+            extras = ''.join(f', {name}: {value}' for name, value in info.items())
+            print(f'step: {step}, time: {elapsed:.0f}s, reward: {reward:.2f}{extras}')
+        if last_update is not None:
+            print(f'step: {step}' + ''.join(f', {name}: {value:.3f}' for name, value in last_update.items()))
+        self.algo.save(os.path.join(self.model_dir, f'step_{step}'))
+        self.algo._env = self.env                      # eval() pointed the algorithm at the test env
+
+    # ---- evaluation -----------------------------------------------------------------------------------------
+    def _episode(self, env) -> Tuple[float, float, torch.Tensor]:
+        """One episode under `algo.apply`: (sum over steps of the mean agent reward, fraction of agents that never collided,
+        per-agent reach flags of the last step)."""
+        never_hit = torch.ones(env.num_agents, dtype=torch.bool)
+        reach = torch.zeros(env.num_agents, dtype=torch.bool)
+        total = 0.0
+        graph = env.reset()
+        done = False
+        while not done:
+            action = self.algo.apply(self._with_u_ref(env, graph))
+            graph, reward, done, info = env.step(action)
+            total += float(np.mean(reward))
+            hit = info.get('collision')
+            if hit is not None and len(hit):
+                never_hit[torch.as_tensor(hit).cpu().long()] = False
+            if 'reach' in info:
+                reach = torch.as_tensor(info['reach']).cpu().bool()
+        return total, float(never_hit.float().mean()), reach
 
     def eval(self, step: int, eval_epi: int) -> Tuple[float, dict]:
-        """Rollouts with the test-time controller `algo.apply` (reference trainer.py:95-141)."""
-        rewards, safes = [], []
-        self.algo._env = self.env_test
+        env = self.env_test
+        self.algo._env = env
+        rewards, safe, reach = [], [], torch.zeros(env.num_agents, dtype=torch.bool)
         for _ in range(eval_epi):
-            data = self.env_test.reset()
-            ep_reward, ep_safe, t = 0., [], 0
-            while True:
-                data.update(Data(u_ref=self.env_test.u_ref(data)))
-                action = self.algo.apply(data)
-                data, reward, done, info = self.env_test.step(action)
-                ep_reward += float(np.mean(reward))
-                ep_safe.append(info['safe'])
-                t += 1
-                if done:
-                    break
-            rewards.append(ep_reward)
-            safes.append(float(np.mean(ep_safe)))
-        self.writer.add_scalar('test/reward', float(np.mean(rewards)), step)
-        self.writer.add_scalar('test/safe_rate', float(np.mean(safes)), step)
-        return float(np.mean(rewards)), {'safe': float(np.mean(safes))}
+            r, s, reach = self._episode(env)
+            rewards.append(r)
+            safe.append(s)
+        mean_reward, mean_safe = float(np.mean(rewards)), float(np.mean(safe))
+        self.writer.add_scalar('test/reward', mean_reward, step)
+        self.writer.add_scalar('test/safe_rate', mean_safe, step)
+        return mean_reward, {'safe': round(mean_safe, 2), 'reach': round(float(reach.float().mean()), 2)}

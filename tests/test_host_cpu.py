@@ -235,3 +235,71 @@ def test_device_replay_matches_list_buffer(monkeypatch):
     check(lst, ring)
     lst.merge(lst2), ring.merge(ring2)
     check(lst, ring)
+
+
+def test_trainer_loop_with_stub_env_and_algo(tmp_path):
+    """gcbf_b200.trainer.Trainer is host glue around env / algo calls: drive it with CPU stubs and check the reference's
+    contract (gcbf/trainer/trainer.py:42-141) -- exploration probability decays linearly from 1, u_ref is attached before the
+    algorithm sees a graph, resets on `done`, update / checkpoint cadence, and eval() reports mean episode reward, the
+    fraction of agents that never collided and the reach fraction of the last step."""
+    import numpy as np
+    import torch
+    from gcbf_b200.data import Data
+    from gcbf_b200.trainer import Trainer
+
+    class Env:
+        num_agents = 4
+
+        def __init__(self, horizon):
+            self.horizon, self.t, self.resets = horizon, 0, 0
+
+        def reset(self):
+            self.t, self.resets = 0, self.resets + 1
+            return Data(states=torch.zeros(4, 2))
+
+        def u_ref(self, graph):
+            return graph.states + 1.0
+
+        def step(self, action):
+            self.t += 1
+            info = {'safe': 1.0, 'reach': torch.tensor([True, False, True, True]),
+                    'collision': torch.tensor([1]) if self.t == 2 else torch.tensor([], dtype=torch.long)}
+            return Data(states=torch.full((4, 2), float(self.t))), np.full(4, 0.5), self.t >= self.horizon, info
+
+    class Algo:
+        def __init__(self):
+            self.probs, self.updates, self.saved, self.seen_u_ref = [], [], [], True
+            self._env = None
+
+        def step(self, graph, prob):
+            self.probs.append(prob)
+            self.seen_u_ref &= hasattr(graph, 'u_ref')
+            return torch.zeros(4, 2)
+
+        def post_step(self, graph, action, reward, done, nxt):
+            self.seen_u_ref &= hasattr(nxt, 'u_ref')
+
+        def is_update(self, step):
+            return step % 4 == 0
+
+        def update(self, step, writer):
+            self.updates.append(step)
+            return {'acc/safe': 1.0}
+
+        def apply(self, graph):
+            self.seen_u_ref &= hasattr(graph, 'u_ref')
+            return torch.zeros(4, 2)
+
+        def save(self, path):
+            self.saved.append(os.path.basename(path))
+
+    env, env_test, algo = Env(horizon=3), Env(horizon=5), Algo()
+    tr = Trainer(env, env_test, algo, str(tmp_path / 'run'))
+    tr.train(steps=8, eval_interval=4, eval_epi=2)
+    assert np.allclose(algo.probs, [1 - k / 8 for k in range(8)]) and algo.seen_u_ref
+    assert algo.updates == [4, 8] and algo.saved == ['step_4', 'step_8']
+    assert env.resets == 1 + 2                       # initial reset + one per finished 3-step episode (steps 3 and 6)
+    assert algo._env is env
+    reward, info = tr.eval(9, 3)
+    assert abs(reward - 5 * 0.5) < 1e-9 and info == {'safe': 0.75, 'reach': 0.75}
+    assert os.path.isdir(tmp_path / 'run' / 'models')
