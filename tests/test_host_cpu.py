@@ -303,3 +303,32 @@ def test_trainer_loop_with_stub_env_and_algo(tmp_path):
     reward, info = tr.eval(9, 3)
     assert abs(reward - 5 * 0.5) < 1e-9 and info == {'safe': 0.75, 'reach': 0.75}
     assert os.path.isdir(tmp_path / 'run' / 'models')
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
+    """Error behaviour of the C ABI (include/gcbf_b200.h): bad arguments return GCBF_E_INVALID (-1) with a message in
+    gcbf_last_error() -- checked here for the tensor-core entry points, whose argument validation runs before any CUDA call, so
+    no GPU is needed.  (Pointers below are never dereferenced on the host.)"""
+    lib = _C.lib()
+    ok_ptr, odd_ptr = 0x7f0000000000, 0x7f0000000004          # 16-byte aligned / misaligned fake device addresses
+
+    def err():
+        return lib.gcbf_last_error().decode()
+
+    # companion buffers must be 16-byte aligned with a pitch that is a multiple of 8 halves
+    assert lib.gcbf_split_f16(ok_ptr, 64, 4, 64, ok_ptr, odd_ptr, 64, None, 0, None) == -1 and 'aligned' in err()
+    assert lib.gcbf_split_f16(ok_ptr, 64, 4, 64, ok_ptr, ok_ptr, 60, None, 0, None) == -1 and ('pitch' in err() or 'bad arguments' in err())
+    assert lib.gcbf_split_f16(ok_ptr, 32, 4, 64, ok_ptr, ok_ptr, 64, None, 0, None) == -1          # ld < cols
+    assert lib.gcbf_amax_f32(ok_ptr, 8, 4, 8, None, 0, None) == -1                                  # no amax slot
+    # GEMM entry points: missing amax words, output pitch smaller than the row, misaligned companions
+    args = dict(Xh=ok_ptr, ldx=64, xa=ok_ptr, Wh=ok_ptr, ldw=64, wa=ok_ptr)
+    assert lib.gcbf_linear_fwd_h(args['Xh'], 64, None, args['Wh'], 64, ok_ptr, None, None, ok_ptr, 256, 512, 256, 64, 0, None, None) == -1
+    assert lib.gcbf_linear_fwd_h(args['Xh'], 64, ok_ptr, args['Wh'], 64, ok_ptr, None, None, ok_ptr, 100, 512, 256, 64, 0, None, None) == -1
+    assert lib.gcbf_linear_fwd_h(odd_ptr, 64, ok_ptr, args['Wh'], 64, ok_ptr, None, None, ok_ptr, 256, 512, 256, 64, 0, None, None) == -1
+    assert 'gcbf_linear_fwd_h' in err()
+    assert lib.gcbf_linear_bwd_data_h(ok_ptr, 256, ok_ptr, ok_ptr, 64, ok_ptr, None, ok_ptr, 32, ok_ptr, 64, 512, 256, 64, 0, None, None) == -1   # ld_relu < K
+    assert lib.gcbf_linear_bwd_weight_h(ok_ptr, 256, ok_ptr, ok_ptr, 62, ok_ptr, None, ok_ptr, 64, 512, 256, 64, 0, None) == -1    # pitch not a multiple of 8
+    assert lib.gcbf_amax_split_batched(None, 3, None) == -1
+    assert lib.gcbf_sn_power_iter_batched(None, 1, ok_ptr, 0, None) == -1
+    # the fp32 entry points keep their "tensor-core path has its own entry point" answer for impl = 2
+    assert lib.gcbf_linear_fwd(ok_ptr, 64, ok_ptr, 64, None, None, ok_ptr, 64, 0, 64, 64, 0, 2, None, None) in (0, -3)
