@@ -2,7 +2,13 @@
 """bench.py -- agent*steps/sec of the GCBF train step (one inner iteration of GCBF.update, reference
 gcbf/algo/gcbf.py:158-226) on synthetic BASELINE.json configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl own|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3] [--also C2,...|none] [--impl own|reference]
+
+Workload     : `value` / `e2e` / `roofline` are measured on --config, by default C3 (DubinsCar n=1024, obs=32, B=64 per GPU) -- the
+               largest single-GPU configuration of BASELINE.json.  `config.also` carries the same device-timed and end-to-end
+               numbers for further BASELINE configs measured in the same run: C2 at every N, and under --gpus 8 the two
+               configurations BASELINE.json defines over 8 GPUs -- C4 (SimpleDrone n=1024, 16 replicas = 2 per GPU) and C5
+               (DubinsCar n=4096 dense, 8 graphs = 1 per GPU, gradient all-reduce).
 
 own arm      : gcbf_b200 (sm_100a kernels through the C ABI).  `value` = device-timed throughput with the batch
                resident in HBM; `e2e` = the same step driven from pinned HOST buffers (H2D of the states, graph
@@ -141,18 +147,11 @@ def build_case(cfg_name, device, rank):
     return sb, env, algo
 
 
-def run_own(args):
-    import torch.distributed as dist
+def measure(cfg_name, args, dev, rank, world, dist, with_roofline, sampler=None):
+    """Device-timed and end-to-end throughput of one BASELINE config on this rank's share (max over ranks taken by the caller)."""
     from gcbf_b200 import _C, ops
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    sb, env, algo = build_case(args.config, dev, rank)
+    sb, env, algo = build_case(cfg_name, dev, rank)
+    algo.process_group = None
     B, n = sb.num_graphs, sb.num_agents
     data = env.graph_from_states(sb.states.to(dev))
     E = int(data.edge_index.shape[1])
@@ -166,8 +165,7 @@ def run_own(args):
     for _ in range(args.warmup):
         algo.train_step(data)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if sampler is not None:
         sampler.start()
     _C.reset_counters()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -179,7 +177,7 @@ def run_own(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = _C.KERNEL_LAUNCHES
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
     scal = res['scalars'].tolist()
     # ---- end-to-end: host buffers in, scalars out, every step ---------------------------------------------------
     host_states = sb.states.pin_memory()
@@ -194,57 +192,109 @@ def run_own(args):
         # losses); every row has landed when the timed region is closed by the synchronize below
         out_host[i].copy_(r['scalars'], non_blocking=True)
 
-    if args.no_e2e:
-        args_e2e_steps = 0
-    else:
-        args_e2e_steps = args.steps
+    e2e_runs = []
+    if not args.no_e2e:
         for i in range(2):
             e2e_step(i)
-    # this leg synchronises with the host twice per step (edge counts), so one host hiccup on a shared box moves a K = 10 total
-    # by tens of percent: the K steps are timed twice back to back and the faster total is reported (both are kept in the line)
-    e2e_runs = []
-    for _rep in range(2 if args_e2e_steps else 1):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args_e2e_steps):
-            e2e_step(2 + i)
-        e1.record()
-        barrier()
-        e2e_runs.append(e0.elapsed_time(e1))
-        assert args_e2e_steps == 0 or bool(torch.isfinite(out_host[2:2 + args_e2e_steps]).all()), 'e2e results did not reach the host'
-    ms_e2e = min(e2e_runs)
+        # this leg synchronises with the host every step (edge counts), so one host hiccup on a shared box moves a K = 10 total
+        # by tens of percent: the K steps are timed three times back to back and the MEDIAN total is reported (all are kept)
+        for _rep in range(3):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.steps):
+                e2e_step(2 + i)
+            e1.record()
+            barrier()
+            e2e_runs.append(e0.elapsed_time(e1))
+            assert bool(torch.isfinite(out_host[2:2 + args.steps]).all()), 'e2e results did not reach the host'
+    ms_e2e = statistics.median(e2e_runs) if e2e_runs else 0.0
 
-    # roofline pass: the same steps again with a CUDA-event pair around every GEMM launch (the ~2000 event records slow
-    # the host down, so this pass is kept out of the throughput measurement above)
-    # The actor's side stream is switched off here: with two streams the GEMMs of the two nets overlap and a per-launch event
-    # pair would time the kernel plus whatever shares the GPU with it.
-    two_streams = os.environ.get('GCBF_TWO_STREAMS')
-    os.environ['GCBF_TWO_STREAMS'] = '0'
-    algo.train_step(data)
-    ops.GEMM_TIMER.enable()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record()
-    for _ in range(args.steps):
+    gemm, ms_instr = None, None
+    if with_roofline:
+        # roofline pass: the same steps again with a CUDA-event pair around every GEMM launch (the event records slow the host
+        # down, so this pass is kept out of the throughput measurement above).  The side stream is switched off here: with two
+        # streams the GEMMs of the two nets overlap and a per-launch event pair would time the kernel plus whatever shares the
+        # GPU with it.
+        two_streams = os.environ.get('GCBF_TWO_STREAMS')
+        os.environ['GCBF_TWO_STREAMS'] = '0'
         algo.train_step(data)
-    ev3.record()
-    barrier()
-    ms_instr = ev2.elapsed_time(ev3)
-    gemm = ops.GEMM_TIMER.summary()
-    ops.GEMM_TIMER.disable()
-    if two_streams is None:
-        del os.environ['GCBF_TWO_STREAMS']
-    else:
-        os.environ['GCBF_TWO_STREAMS'] = two_streams
+        ops.GEMM_TIMER.enable()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        for _ in range(args.steps):
+            algo.train_step(data)
+        ev3.record()
+        barrier()
+        ms_instr = ev2.elapsed_time(ev3)
+        gemm = ops.GEMM_TIMER.summary()
+        ops.GEMM_TIMER.disable()
+        if two_streams is None:
+            del os.environ['GCBF_TWO_STREAMS']
+        else:
+            os.environ['GCBF_TWO_STREAMS'] = two_streams
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
+    # edges of all ranks (every rank owns different graphs)
+    et = torch.tensor([E], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(et)
+    del algo, data
+    return dict(sb=sb, B=B, n=n, E=E, E_total=int(et.item()), ms=ms, ms_e2e=ms_e2e, e2e_runs=e2e_runs, h2d=h2d, launches=launches, clocks=clocks,
+                scal=scal, gemm=gemm, ms_instr=ms_instr)
+
+
+def shape_traffic(dom):
+    """DRAM bytes per launch of the dominant launch shape from the committed `ncu --set full` capture of exactly that shape
+    (profiles/r02_gemm_h_ncu_full.json: {"launches": [{"product", "M", "N", "K", "dram_read_bytes", "dram_write_bytes"}, ...]});
+    None when no capture of this shape exists -- never a number taken from a different launch."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_gemm_h_ncu_full.json')) as f:
+            caps = json.load(f)['launches']
+    except Exception:
+        return None, None
+    for c in caps:
+        if c.get('product') == dom['product'] and (c.get('M'), c.get('N'), c.get('K')) == (dom['M'], dom['N'], dom['K']):
+            return int(c['dram_read_bytes'] + c['dram_write_bytes']), c.get('source', 'profiles/r02_gemm_h_ncu_full.json')
+    return None, None
+
+
+def run_own(args):
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    main_cfg = args.config
+    if args.also == 'auto':
+        also = [c for c in (['C2'] + (['C4', 'C5'] if world == 8 else [])) if c != main_cfg]
+    else:
+        also = [c for c in args.also.split(',') if c and c != 'none' and c != main_cfg]
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    m = measure(main_cfg, args, dev, rank, world, dist, True, sampler)
+    extra = {}
+    for c in also:
+        r = measure(c, args, dev, rank, world, dist, False, None)
+        agents_c = r['B'] * r['n'] * world
+        extra[c] = {'workload': f"{c}: {r['sb'].env} n={r['n']} obs={r['sb'].num_obs} B={r['B']}/GPU area={r['sb'].area_size}",
+                    'agents_per_step': agents_c, 'edges_per_step': r['E_total'], 'ms_per_step': round(r['ms'] / args.steps, 4),
+                    'value': round(agents_c * args.steps / (r['ms'] / 1e3), 1), 'unit': UNIT,
+                    'e2e': ({'value': round(agents_c * args.steps / (r['ms_e2e'] / 1e3), 1), 'ms_per_step': round(r['ms_e2e'] / args.steps, 4),
+                             'h2d_bytes_per_step': r['h2d'], 'd2h_bytes_per_step': 32} if r['e2e_runs'] else None),
+                    'gpu_launches': r['launches'], 'loss': round(r['scal'][6], 6)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    sb, B, n, E, ms, ms_e2e, gemm, ms_instr = m['sb'], m['B'], m['n'], m['E'], m['ms'], m['ms_e2e'], m['gemm'], m['ms_instr']
     peaks = read_peaks()
     agents = B * n * world
     value = agents * args.steps / (ms / 1e3)
@@ -262,12 +312,14 @@ def run_own(args):
                 'launches_timed': gemm['launches'], 'gemm_share_of_step': round(gemm['ms'] / ms_instr, 4),
                 'prep_share_of_step': round(gemm.get('prep_ms', 0.0) / ms_instr, 4),
                 'instrumented_ms_per_step': round(ms_instr / args.steps, 4),
+                'whole_step_flops': gemm['flops'] / args.steps,
+                'whole_step_frac': round(gemm['flops'] / args.steps / (ms / args.steps) / 1e9 / f16_peak, 4),
                 'instrumented_pass': 'single stream, CUDA-event pair per GEMM / operand-prep launch', 'traffic': None}
     dom = gemm.get('dominant')
     if dom:
         # the launch shape that takes the most GEMM time: algorithmic FLOPs and bytes per launch (companions in: 2 planes x
-        # 2 B per element of each operand; fp32 out) against its CUDA-event duration; DRAM traffic of exactly this launch shape
-        # from the committed `ncu --set full` capture (profiles/), not from this run
+        # 2 B per element of each operand; fp32 out) against its CUDA-event duration; DRAM traffic only from a committed
+        # `ncu --set full` capture of exactly this launch shape
         M_, N_, K_ = dom['M'], dom['N'], dom['K']
         out_elems = {'forward': M_ * N_, 'data-grad': M_ * K_, 'weight-grad': N_ * K_}[dom['product']]
         in_elems = {'forward': M_ * K_ + N_ * K_, 'data-grad': M_ * N_ + N_ * K_, 'weight-grad': M_ * N_ + M_ * K_}[dom['product']]
@@ -278,33 +330,28 @@ def run_own(args):
             'flops_per_launch': dom['flops_per_launch'], 'ms_per_launch': round(dom['ms_per_launch'], 4),
             'achieved': round(tf, 1), 'frac': round(tf / f16_peak, 4), 'frac_issued': round(3 * tf / f16_peak, 4),
             'algorithmic_bytes_per_launch': alg_bytes}
-        try:
-            with open(os.path.join(ROOT, 'profiles', 'r01_gemm_h_ncu_full.json')) as f:
-                cap = json.load(f)['launches'][0]
-            rd, wr = float(cap['dram_read'].split()[0]), float(cap['dram_write'].split()[0])
-            roofline['traffic'] = round((rd + wr) * 1e6)
-            roofline['traffic_source'] = ('dram__bytes_read.sum + dram__bytes_write.sum of one forward M=24196 N=2048 K=2048 launch, '
-                                          'profiles/r01_gemm_h_ncu_full.json (ncu --set full)')
-        except Exception:
-            pass
+        roofline['traffic'], src = shape_traffic(dom)
+        if src:
+            roofline['traffic_source'] = src
     line = {
         'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': round(ms / args.steps, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32 via 3xfp16 tensor-core products (fp32 accumulate)' if gemm['tensor'] else 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.config}: {sb.env} n={n} obs={sb.num_obs} B={B}/GPU area={sb.area_size}',
+        'config': {'workload': f'{main_cfg}: {sb.env} n={n} obs={sb.num_obs} B={B}/GPU area={sb.area_size}',
                    'agents_per_step': agents, 'edges_per_gpu': E, 'parallelism': f'dp{world}',
                    'l2': 'no flush: per-step working set (>= 0.2 GB of activations per 2048-wide layer + 98 MB weights) '
-                         'exceeds the 126 MB L2'},
-        'clocks': clocks,
-        'e2e': ({'value': round(agents * args.steps / (ms_e2e / 1e3), 1), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-                 'd2h_bytes_per_step': 32, 'ms_per_step': round(ms_e2e / args.steps, 4),
-                 'ms_per_step_runs': [round(x / args.steps, 4) for x in e2e_runs]} if args_e2e_steps else None),
-        'gpu_launches': launches,
+                         'exceeds the 126 MB L2',
+                   'also': extra},
+        'clocks': m['clocks'],
+        'e2e': ({'value': round(agents * args.steps / (ms_e2e / 1e3), 1), 'unit': UNIT, 'h2d_bytes_per_step': m['h2d'],
+                 'd2h_bytes_per_step': 32, 'ms_per_step': round(ms_e2e / args.steps, 4), 'statistic': 'median of 3 timed K-step runs',
+                 'ms_per_step_runs': [round(x / args.steps, 4) for x in m['e2e_runs']]} if m['e2e_runs'] else None),
+        'gpu_launches': m['launches'],
         'roofline': roofline,
-        'loss': round(scal[6], 6),
+        'loss': round(m['scal'][6], 6),
     }
     if world == 1 and not args.no_cpu_baseline:
-        line['cpu_baseline'] = cpu_baseline(args.config, budget_s=20.0)
+        line['cpu_baseline'] = cpu_baseline(main_cfg, budget_s=25.0)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -366,29 +413,40 @@ def cpu_baseline(cfg_name, budget_s=20.0):
 
 
 def run_reference(args):
+    """Reference arm: the reference's algorithm (oracle port, kind "port": torch_geometric cannot be installed on the box) on
+    the host cores, same config / metric / K / W as the own arm.  Every step runs as many of the config's graphs as fit a
+    ~150 s budget for the whole K + W run (all of them when that fits: C2 does, C3's 64 graphs do not)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from gcbf_b200 import synth
     full = synth.GRAPHS_PER_GPU[args.config]
-    graphs = max(1, min(full, 4))
-    step, sb = cpu_sample_step(args.config, graphs)
-    for _ in range(min(args.warmup, 1)):
+    steps, warmup = args.steps, args.warmup
+    probe = min(full, 2)
+    step, sb = cpu_sample_step(args.config, probe)
+    step()
+    t0 = time.perf_counter()
+    step()
+    per_graph = (time.perf_counter() - t0) / probe
+    budget = float(os.environ.get('GCBF_REF_BUDGET_S', '150'))
+    graphs = int(max(1, min(full, budget / max(1, steps + warmup) / per_graph)))
+    if graphs != probe:
+        step, sb = cpu_sample_step(args.config, graphs)
+    for _ in range(warmup):
         step()
-    steps = min(args.steps, 5)
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
     value = graphs * sb.num_agents * steps / dt
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    sample = (f'all {full} graphs per step' if graphs == full else f'{graphs} of {full} graphs per step (bounded sample)') + f', {steps} steps'
     line = {'impl': 'reference', 'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': steps,
-            'warmup': min(args.warmup, 1), 'ms_per_step': round(dt / steps * 1e3, 2), 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': warmup, 'ms_per_step': round(dt / steps * 1e3, 2), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{args.config}: {sb.env} n={sb.num_agents} obs={sb.num_obs}; bounded sample of {graphs} of '
-                                   f'{full} graphs per step on the host CPU'},
-            'cpu_baseline': {'value': round(value, 1), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                             'sample': f'{graphs} of {full} graphs per step, {steps} steps'},
+            'config': {'workload': f'{args.config}: {sb.env} n={sb.num_agents} obs={sb.num_obs} B={full}/GPU area={sb.area_size}',
+                       'graphs_per_step': graphs, 'graphs_in_config': full, 'same_config': graphs == full},
+            'cpu_baseline': {'value': round(value, 1), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
             'e2e': {'value': round(value, 1), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -399,7 +457,8 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--config', default='C2')
+    ap.add_argument('--config', default='C3', help='BASELINE config `value` is measured on (default: the largest single-GPU one)')
+    ap.add_argument('--also', default='auto', help="further configs reported under config.also: comma list, 'none', or 'auto' (C2; plus C4, C5 at 8 GPUs)")
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (profiling runs under ncu only)')

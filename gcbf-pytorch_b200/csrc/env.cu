@@ -98,7 +98,7 @@ __global__ void u_ref_kernel(EnvCfg c, const float* __restrict__ states, int ld,
   const int g = a / c.n, il = a % c.n;
   const int sd = c.env == GCBF_ENV_SIMPLE_DRONE ? 6 : 4;
   const int ad = c.env == GCBF_ENV_SIMPLE_DRONE ? 3 : 2;
-  float s[6], gl[6], u[3];
+  float s[6], gl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, u[3];   // goal rows narrower than 6 read as zeros
   for (int k = 0; k < sd; ++k) s[k] = states[((size_t)g * c.N + il) * ld + k];
   for (int k = 0; k < ld_goal && k < 6; ++k) gl[k] = goal[(size_t)il * ld_goal + k];
   u_ref_one(c, s, gl, K, u);
@@ -120,7 +120,7 @@ __global__ void step_fwd_kernel(EnvCfg c, const float* __restrict__ states, int 
   bool frozen = false;
   if (is_agent) {
     const int a = g * c.n + l;
-    float gl[6], ur[3];
+    float gl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ur[3];
     for (int k = 0; k < ld_goal && k < 6; ++k) gl[k] = goal[(size_t)l * ld_goal + k];
     u_ref_one(c, s, gl, K, ur);
     for (int k = 0; k < ad; ++k) {

@@ -238,10 +238,11 @@ class GCBF(Algorithm):
                    safe_mask=masks[0], unsafe_mask=masks[1], edge_index_new=relinked.edge_index, hdot=hdot)
         if compute_acc_h_dot:                                            # gcbf.py:209 (M x M broadcast mean)
             cnt = torch.empty(1, device=dev, dtype=torch.int64)
-            hdot_all = red.gather_cat(hdot)
+            sizes = red.sizes(M)                                         # ranks may own different numbers of agents
+            hdot_all = red.gather_cat(hdot, sizes)
             _C.call('gcbf_pair_count', _C.ptr(hdot_all), hdot_all.numel(), _C.ptr(hd), M, float(hp['alpha']), _C.ptr(cnt))
             red.sum_(cnt)
-            out['acc_h_dot'] = cnt.to(torch.float64) / float(world * M) / float(world * M)
+            out['acc_h_dot'] = cnt.to(torch.float64) / float(sum(sizes)) / float(sum(sizes))
 
         red.sum_(bucket.grad)                                            # the ONE gradient collective (K9)
         if apply_optim:
@@ -341,8 +342,9 @@ class GCBF(Algorithm):
     # ---- checkpoints (file names and keys of gcbf.py:249-258) ------------------------------------------
     def save(self, save_dir: str):
         os.makedirs(save_dir, exist_ok=True)
-        torch.save(self.cbf.state_dict(), os.path.join(save_dir, 'cbf.pkl'))
-        torch.save(self.actor.state_dict(), os.path.join(save_dir, 'actor.pkl'))
+        # parameters are views into the flat bucket: clone them, or each file would serialise the whole bucket storage
+        for mod, name in ((self.cbf, 'cbf.pkl'), (self.actor, 'actor.pkl')):
+            torch.save({k: v.detach().clone() for k, v in mod.state_dict().items()}, os.path.join(save_dir, name))
 
     def load(self, load_dir: str):
         assert os.path.exists(load_dir)

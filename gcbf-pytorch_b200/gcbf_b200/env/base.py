@@ -59,6 +59,7 @@ class MultiAgentEnv(ABC):
     POS_DIM = 2
     RADIUS_KEY = 'car_radius'
     GRAPH_METRIC = 1          # 0: squared distance (torch_cluster), 1: torch.norm then compare
+    GOAL_DIM = 2              # goal columns the kernels read (SimpleCar 2, DubinsCar 2, SimpleDrone 6)
 
     def __init__(self, num_agents: int, device: torch.device, dt: float = 0.03, params: Optional[dict] = None,
                  max_neighbors: Optional[int] = None):
@@ -143,8 +144,14 @@ class MultiAgentEnv(ABC):
         return None
 
     def set_goal(self, goal: Tensor):
-        """Install the goal set [num_agents, goal_dim] (the reference keeps it in `env._goal`)."""
-        self._goal = goal.to(self._device, torch.float32).contiguous()
+        """Install the goal set [num_agents, goal_dim] (the reference keeps it in `env._goal`).  Rows narrower than the
+        kernels read (SimpleDrone: 6 columns, position + zero velocity) are zero-padded; fewer than POS_DIM columns raise."""
+        goal = goal.to(self._device, torch.float32)
+        if goal.dim() != 2 or goal.shape[0] != self._num_agents or goal.shape[1] < self.POS_DIM:
+            raise ValueError(f'goal must be [{self._num_agents}, >= {self.POS_DIM}], got {tuple(goal.shape)}')
+        if goal.shape[1] < self.GOAL_DIM:
+            goal = torch.cat([goal, goal.new_zeros(goal.shape[0], self.GOAL_DIM - goal.shape[1])], dim=1)
+        self._goal = goal.contiguous()
 
     # ---- hot path ------------------------------------------------------------------------------------
     def edge_attr(self, state: Tensor, edge_index: Tensor) -> Tensor:

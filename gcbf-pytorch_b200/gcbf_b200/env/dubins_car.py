@@ -69,4 +69,4 @@ class DubinsCar(MultiAgentEnv):
         return self._data
 
     def _reward(self, action, reach, prev_reach, collision):
-        return (reach.int() - prev_reach.int()) * 10 - collision.int() * 0.1 - 0.0001 - torch.norm(action, dim=1) * 0.0001
+        return (reach.int() - prev_reach.int()) * 10 - collision.int() * 0.1 - 0.0001 - torch.norm(action, dim=1).sum() * 0.01   # dubins_car.py:535 (summed over agents)

@@ -14,6 +14,7 @@ from .base import MultiAgentEnv, lqr
 class SimpleDrone(MultiAgentEnv):
     ENV_NAME = 'SimpleDrone'
     POS_DIM = 3
+    GOAL_DIM = 6
     RADIUS_KEY = 'drone_radius'
     GRAPH_METRIC = 1
 

@@ -26,7 +26,7 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_cases():
-    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt'))
+    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and not f.startswith('pretrained'))
 
 
 def load_golden(name):

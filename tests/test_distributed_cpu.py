@@ -51,6 +51,13 @@ def _worker(rank, world, port, tmp):
         # 2. h_dot gather keeps rank order
         hd = red.gather_cat(h[sl].clone())
         assert torch.equal(hd, h)
+        # 2b. unequal shards (B not divisible by world): sizes travel on the host, the gather drops the padding
+        B2 = 7
+        lo2, hi2 = shard_range(B2, world, rank)
+        h2 = torch.arange(B2 * n, dtype=torch.float32)
+        sizes = red.sizes((hi2 - lo2) * n)
+        assert sizes == [(b - a) * n for a, b in (shard_range(B2, world, r) for r in range(world))] and sum(sizes) == B2 * n
+        assert torch.equal(red.gather_cat(h2[lo2 * n:hi2 * n].clone(), sizes), h2)
         # 3. one flat-bucket all-reduce == sum of the per-rank gradients; weights stay replicated
         from gcbf_b200.algo.gcbf import _FlatBucket
         torch.manual_seed(3)

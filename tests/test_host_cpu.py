@@ -106,6 +106,33 @@ def test_state_dict_key_contract():
     assert act.state_dict()['feat_2_action.net.0.weight'].shape == (512, 1026)
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/pretrained'), reason='shipped checkpoints live in the reference checkout')
+@pytest.mark.parametrize('env_name', ['SimpleCar', 'DubinsCar', 'SimpleDrone'])
+def test_shipped_checkpoints_load_strictly(env_name, tmp_path):
+    """All six shipped checkpoint files (pretrained/<env>/models/step_500000/{cbf,actor}.pkl) load with
+    strict=True into the product modules through GCBF.load, also AFTER the parameters were re-homed into the flat bucket, and
+    GCBF.save writes files of the reference's size (no bucket-sized storages) that the oracle port reads back unchanged."""
+    from gcbf_b200.synth import seeded_algo
+    ckpt = f'/root/reference/pretrained/{env_name}/models/step_500000'
+    env, algo = seeded_algo(env_name, 16, torch.device('cpu'))
+    algo._ensure_bucket()                               # parameters become views into the flat bucket
+    algo.load(ckpt)
+    want_c = torch.load(os.path.join(ckpt, 'cbf.pkl'), map_location='cpu')
+    want_a = torch.load(os.path.join(ckpt, 'actor.pkl'), map_location='cpu')
+    for mod, want in ((algo.cbf, want_c), (algo.actor, want_a)):
+        sd = mod.state_dict()
+        assert list(sd.keys()) == list(want.keys())
+        for k in want:
+            assert torch.equal(sd[k], want[k]), k
+    assert algo.cbf.feat_transformer.module_0.phi.net[2].weight_orig.data_ptr() >= algo._bucket.flat.data_ptr()   # still a bucket view
+    algo.save(str(tmp_path))
+    for f, want in (('cbf.pkl', want_c), ('actor.pkl', want_a)):
+        size = os.path.getsize(tmp_path / f)
+        assert abs(size - os.path.getsize(os.path.join(ckpt, f))) < 65536, (f, size)      # not 2x: each file holds ONE net
+        back = torch.load(tmp_path / f, map_location='cpu')
+        assert all(torch.equal(back[k], want[k]) for k in want)
+
+
 def test_flat_bucket_views_survive_load_state_dict():
     from gcbf_b200.algo import make_algo
     from gcbf_b200.env import make_env

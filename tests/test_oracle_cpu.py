@@ -224,3 +224,29 @@ json.dump(out, open({str(tmp_path / 'out.json')!r}, 'w'))
     assert got == want
     assert got_ring == want[:-1]
     assert [ring.size, ring.safe_data[-3:], ring.unsafe_data[-3:]] == want[-1]
+
+
+@pytest.mark.parametrize('env_name,n,obs,B,area', [('DubinsCar', 12, 3, 5, 2.0), ('SimpleCar', 10, 0, 4, 1.5), ('SimpleDrone', 6, 6, 3, 1.0)])
+def test_chunked_forward_step_matches_update_step(env_name, n, obs, B, area):
+    """oracle.forward_step_chunked (used by the full-size GPU parity tests) against oracle.update_step on a batch small enough
+    for both: same h / actions / h_next / h_next_new / masks / re-linked edges / losses, same spectral-norm state afterwards."""
+    import copy
+    from gcbf_b200 import synth
+    sb = synth.make_states(env_name, n, obs, B, area, 91)
+    ob = oracle_batch(sb)
+    _, algo = seeded_algo(env_name, n, torch.device('cpu'), 3, {'num_obs': sb.num_obs, 'area_size': area})
+    cbf_a, act_a = sd_clone(algo.cbf), sd_clone(algo.actor)
+    cbf_b, act_b = copy.deepcopy(cbf_a), copy.deepcopy(act_a)
+    want = O.update_step(env_name, cbf_a, act_a, {}, {}, sb.states, sb.goals, ob['edge_index'], ob['u_ref'], B, n, sb.num_obs,
+                         K=ob['K'], apply_optim=False)
+    got = O.forward_step_chunked(env_name, cbf_b, act_b, sb.states, sb.goals, ob['edge_index'], ob['u_ref'], B, n, sb.num_obs,
+                                 K=ob['K'], chunk_graphs=2)
+    assert torch.equal(got['edge_index_new'], want['edge_index_new'])
+    assert torch.equal(got['unsafe_mask'], want['unsafe_mask']) and torch.equal(got['safe_mask'], want['safe_mask'])
+    for k in ('h', 'actions', 'h_next', 'h_next_new', 'states_next'):
+        assert (got[k].reshape(-1) - want[k].reshape(-1)).abs().max().item() <= 2e-7, k       # batched vs chunked GEMM blocking
+    for k in ('loss_unsafe', 'loss_safe', 'loss_h_dot', 'loss_action', 'loss'):
+        assert abs(float(got[k]) - float(want[k])) <= 1e-7, k
+    for k in cbf_a:
+        if k.endswith(('weight_u', 'weight_v')):
+            assert torch.equal(cbf_a[k], cbf_b[k]), k
