@@ -176,7 +176,7 @@ def measure(cfg_name, args, dev, rank, world, dist, with_roofline, sampler=None)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = _C.KERNEL_LAUNCHES
+    launches = _C.kernel_launches()
     clocks = sampler.stop() if sampler is not None else None
     scal = res['scalars'].tolist()
     # ---- end-to-end: host buffers in, scalars out, every step ---------------------------------------------------

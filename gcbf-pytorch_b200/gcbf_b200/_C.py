@@ -5,7 +5,7 @@ call fails, a RuntimeError is raised (the product path must never silently run o
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_ulonglong, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 import torch
 
@@ -36,6 +36,8 @@ P = c_void_p  # every device pointer travels as void*
 _SIGS = {
     'gcbf_last_error': (c_char_p, []),
     'gcbf_abi_version': (c_int, []),
+    'gcbf_abi_struct_size': (c_size_t, [c_int]),
+    'gcbf_launch_count': (c_longlong, [c_int]),
     'gcbf_has_tcgen05': (c_int, []),
     'gcbf_last_gemm_impl': (c_int, []),
     'gcbf_radius_graph_count': (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P, P]),
@@ -97,6 +99,18 @@ def lib():
     return _lib
 
 
+def register(sigs: dict):
+    """Add entry-point signatures (the chain-level ABI is declared next to its ctypes structures in native.py)."""
+    global EXPORTED_SYMBOLS
+    _SIGS.update(sigs)
+    EXPORTED_SYMBOLS = tuple(_SIGS)
+    if _lib is not None:
+        for name, (res, args) in sigs.items():
+            f = getattr(_lib, name)
+            f.restype = res
+            f.argtypes = args
+
+
 def ptr(t):
     """device pointer of a tensor (None -> NULL)."""
     if t is None:
@@ -133,6 +147,13 @@ def reset_counters():
     global KERNEL_LAUNCHES, ABI_CALLS
     KERNEL_LAUNCHES = 0
     ABI_CALLS = 0
+    lib().gcbf_launch_count(1)
+
+
+def kernel_launches() -> int:
+    """Kernels launched since reset_counters(): by per-kernel entry points called from Python (counted here) and by the
+    chain-level entry points (counted inside the library, csrc/net.cu)."""
+    return KERNEL_LAUNCHES + int(lib().gcbf_launch_count(0))
 
 
 _FN = {}

@@ -153,7 +153,10 @@ class GCBF(Algorithm):
     def train_step(self, graphs, apply_optim: bool = True, compute_acc_h_dot: bool = True) -> Dict[str, Tensor]:
         """One inner iteration of GCBF.update (gcbf.py:158-226) on a collated batch.  Returns device tensors
         (no host sync): 'scalars' = [loss_unsafe, loss_safe, loss_h_dot, loss_action, acc_unsafe, acc_safe,
-        total_loss, num_agents], 'acc_h_dot', plus h / actions / h_next / h_next_new for inspection."""
+        total_loss, num_agents], 'acc_h_dot', plus h / actions / h_next / h_next_new for inspection (views into the step's
+        workspace: valid until the next train_step of this object)."""
+        if ops.NATIVE:
+            return self._train_step_native(graphs, apply_optim, compute_acc_h_dot)
         from ..arena import ARENA
         ARENA.begin(graphs.states.device)      # every activation / gradient below is a view into the step arena
         try:
@@ -249,12 +252,123 @@ class GCBF(Algorithm):
             self.optim_step()
         return out
 
+    # ---- the train step through the chain-level C ABI (csrc/step.cu): three calls, two collectives in between ----------------
+    def _step_desc(self):
+        """gcbf_step_desc of this algorithm: built once (parameter / gradient / companion pointers are stable: they are views
+        into the flat bucket), the per-step fields are refreshed by the caller."""
+        import ctypes
+        from .. import native
+        env, hp = self._env, self.params
+        bucket = self._ensure_bucket()
+        key = (id(env), id(env._goal), env._goal.data_ptr() if env._goal is not None else 0, bucket.flat.data_ptr())
+        cached = getattr(self, '_native_desc', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        cbf_layer, act_layer = self.cbf.feat_transformer.module_0, self.actor.feat_transformer.module_0
+        cbf_spec, act_spec = cbf_layer.net_spec(self.cbf.feat_2_CBF), act_layer.net_spec(self.actor.feat_2_action)
+        d = native.StepDesc()
+        ctypes.memmove(ctypes.byref(d.cbf), ctypes.byref(native.make_net_desc(cbf_spec, 0, 'param')), ctypes.sizeof(native.NetDesc))
+        ctypes.memmove(ctypes.byref(d.actor), ctypes.byref(native.make_net_desc(act_spec, self.action_dim, 'param')),
+                       ctypes.sizeof(native.NetDesc))
+        goal, ldg = ops._mat(env._goal)
+        gain = env._gain()
+        d.goal, d.lqr_gain, d.ld_goal = goal.data_ptr(), (gain.data_ptr() if gain is not None else None), ldg
+        d.state_dim, d.pos_dim, d.action_dim = env.state_dim, env.POS_DIM, self.action_dim
+        d.graph_metric, d.comm_radius = env.GRAPH_METRIC, float(env._params['comm_radius'])
+        d.alpha, d.eps = float(hp['alpha']), float(hp['eps'])
+        d.coef_unsafe, d.coef_safe = float(hp['loss_unsafe_coef']), float(hp['loss_safe_coef'])
+        d.coef_hdot, d.coef_action = float(hp['loss_h_dot_coef']), float(hp['loss_action_coef'])
+        d.grad_bucket, d.grad_bucket_floats = bucket.grad.data_ptr(), bucket.grad.numel()
+        keep = (goal, gain, cbf_spec, act_spec)
+        self._native_desc = (key, (d, keep, cbf_spec.all_layers(), act_spec.all_layers()))
+        return self._native_desc[1]
+
+    def _train_step_native(self, graphs, apply_optim: bool, compute_acc_h_dot: bool) -> Dict[str, Tensor]:
+        import ctypes
+        from .. import native
+        from ..nn.gnn import cached_rowptr
+        env = self._env
+        bucket = self._ensure_bucket()
+        red = self._reducer()
+        dev = graphs.states.device
+        d, _keep, cbf_layers, act_layers = self._step_desc()
+        ops.sync_gemm_impl()
+        d.cbf.refresh_weights = 1 if native._weights_stale(cbf_layers) else 0
+        d.actor.refresh_weights = 1 if native._weights_stale(act_layers) else 0
+        B = env._num_graphs_of(graphs)
+        cfg = env._cfg(B)
+        ctypes.memmove(ctypes.byref(d.env), ctypes.byref(cfg), ctypes.sizeof(_C.EnvCfg))
+        st, ld = ops._mat(graphs.states.detach())
+        x, ea, ei = graphs.x.contiguous(), graphs.edge_attr.detach().contiguous(), graphs.edge_index.contiguous()
+        uref = graphs.u_ref.contiguous()
+        rows = agent_row_index(graphs)
+        rowptr = cached_rowptr(graphs.edge_index, x.shape[0])
+        M, E = int(uref.shape[0]), int(ei.shape[1])
+        b = native.StepBatch()
+        b.states, b.ld_state, b.x = st.data_ptr(), ld, x.data_ptr()
+        b.edge_attr, b.edge_index = (ea.data_ptr(), ei.data_ptr()) if E else (None, None)
+        b.rowptr, b.u_ref, b.row_index = rowptr.data_ptr(), uref.data_ptr(), (rows.data_ptr() if rows is not None else None)
+        b.num_edges, b.num_nodes, b.num_agents_total = E, int(x.shape[0]), M
+        bufs = getattr(self, '_native_ws', None)
+        if bufs is None:
+            bufs = self._native_ws = (native.GrowBuffer(), native.GrowBuffer())
+        need = native.fn('gcbf_step_workspace_bytes')(ctypes.byref(d), ctypes.byref(b))
+        if need == 0:
+            native.check(-1, 'gcbf_step_workspace_bytes')
+        ws = bufs[0].get(need, dev)
+        ctx, out = native.StepCtx(), native.StepOut()
+        main = _C.stream()
+        side_t = self._side_stream(dev, E)
+        side = side_t.cuda_stream if side_t is not None else None
+        native.check(native.fn('gcbf_step_forward')(ctypes.byref(d), ctypes.byref(b), ws.data_ptr(), ws.numel(), ctypes.byref(ctx),
+                                                   ctypes.byref(out), main, side), 'gcbf_step_forward')
+        native._mark_fresh(cbf_layers)
+        native._mark_fresh(act_layers)
+        # the re-linked value pass: its workspace is sized for the previous step's edge count (+ head-room); the call reports the
+        # exact need BEFORE launching anything, so a too small buffer costs one retry, not a wrong result
+        needed = ctypes.c_size_t(0)
+        ws2 = bufs[1].get(max(1, bufs[1].buf.numel() if bufs[1].buf is not None else need // 6), dev)
+        rc = native.fn('gcbf_step_relink')(ctypes.byref(d), ctypes.byref(b), ctypes.byref(ctx), ws2.data_ptr(), ws2.numel(),
+                                           ctypes.byref(needed), ctypes.byref(out), main, side)
+        if rc == native.E_WORKSPACE:
+            ws2 = bufs[1].get(needed.value, dev)
+            rc = native.fn('gcbf_step_relink')(ctypes.byref(d), ctypes.byref(b), ctypes.byref(ctx), ws2.data_ptr(), ws2.numel(),
+                                               ctypes.byref(needed), ctypes.byref(out), main, side)
+        native.check(rc, 'gcbf_step_relink')
+        partial = native.view(ws, out.partial, (16,), torch.float64)
+        red.sum_(partial)                                                # global counts => global masked means
+        native.check(native.fn('gcbf_step_backward')(ctypes.byref(d), ctypes.byref(b), ctypes.byref(ctx), ctypes.byref(out), main, side),
+                     'gcbf_step_backward')
+        a_dim = self.action_dim
+        En = int(out.num_edges_new)
+        res = dict(scalars=native.view(ws, out.scalars, (8,), torch.float32), h=native.view(ws, out.h, (M, 1), torch.float32),
+                   actions=native.view(ws, out.actions, (M, a_dim), torch.float32), h_next=native.view(ws, out.h_next, (M, 1), torch.float32),
+                   h_next_new=native.view(ws, out.h_next_new, (M,), torch.float32),
+                   safe_mask=native.view(ws, out.safe, (M,), torch.uint8).view(torch.bool),
+                   unsafe_mask=native.view(ws, out.unsafe, (M,), torch.uint8).view(torch.bool),
+                   edge_index_new=(native.view(ws2, out.edge_index_new, (2, En), torch.int64) if En else
+                                   torch.empty(2, 0, device=dev, dtype=torch.int64)),
+                   hdot=native.view(ws, out.hdot, (M,), torch.float32))
+        if compute_acc_h_dot:                                            # gcbf.py:209 (M x M broadcast mean)
+            cnt = torch.empty(1, device=dev, dtype=torch.int64)
+            sizes = red.sizes(M)
+            hdot_all = red.gather_cat(res['hdot'], sizes)
+            _C.call('gcbf_pair_count', _C.ptr(hdot_all), hdot_all.numel(), _C.ptr(res['h']), M, float(self.params['alpha']), _C.ptr(cnt))
+            red.sum_(cnt)
+            res['acc_h_dot'] = cnt.to(torch.float64) / float(sum(sizes)) / float(sum(sizes))
+        red.sum_(bucket.grad)                                            # the ONE gradient collective (K9)
+        if apply_optim:
+            self.optim_step()
+        return res
+
     def optim_step(self):
         """clip_grad_norm_(1e-3) per net + Adam (gcbf.py:223-226), fused, on the flat bucket."""
         b = self._ensure_bucket()
         b.step += 1
         b.sumsq.zero_()
         ops.WEIGHT_EPOCH += 1                 # the kernel below rewrites the parameters: fp16 weight companions are stale
+        from .. import native
+        native.WEIGHT_EPOCH += 1
         for i, lr in enumerate((self.lr_cbf, self.lr_actor)):
             lo, hi = b.ranges[i]
             g = b.grad[lo:hi]

@@ -163,6 +163,8 @@ class MultiAgentEnv(ABC):
         ei, _ = ops.radius_graph(data.states.detach(), self.POS_DIM, B, self.nodes_per_graph, self._num_agents,
                                  self._params['comm_radius'], self.GRAPH_METRIC)
         data.update(Data(edge_index=ei, edge_attr=self.edge_attr(data.states, ei)))
+        from ..nn.gnn import prime_rowptr
+        prime_rowptr(ei, int(data.states.shape[0]))      # the CSR the GNN passes need: known sorted, no check / host sync later
         return data
 
     def u_ref(self, data) -> Tensor:

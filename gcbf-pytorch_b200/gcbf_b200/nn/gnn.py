@@ -57,6 +57,17 @@ def cached_rowptr(edge_index: Tensor, num_nodes: int) -> Tensor:
     return rowptr
 
 
+def prime_rowptr(edge_index: Tensor, num_nodes: int) -> Tensor:
+    """CSR row pointer for an edge_index the kernels just produced (radius graph: target-sorted by construction), entered into
+    the cache WITHOUT the sortedness check -- the check reads a device flag back, i.e. costs a host sync per new graph."""
+    rowptr = ops.rowptr_from_edge_index(edge_index, num_nodes, check_sorted=False)
+    if len(_ROWPTR_CACHE) > 64:
+        _ROWPTR_CACHE.clear()
+    key = (id(edge_index), edge_index.data_ptr(), edge_index.shape[1], edge_index._version, num_nodes)
+    _ROWPTR_CACHE[key] = (weakref.ref(edge_index), rowptr)
+    return rowptr
+
+
 class _GNNLayerBase(nn.Module):
     limit_lip = False
 

@@ -10,16 +10,21 @@ autograd.Functions the nn.Modules are built from.
 torch is used for device memory (torch.empty / zeros), streams and autograd bookkeeping only; every
 arithmetic step is a kernel of libgcbf_b200.so.  No CPU fallback: CPU tensors raise.
 """
+import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from . import _C
+from . import _C, native
 from .arena import ARENA, empty as _empty, zeros as _zeros
 from ._C import call, ptr
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+# GCBF_NATIVE=0 keeps the per-kernel Python sequencing of round 1 (net_forward / net_backward below) instead of the chain-level
+# entry points of the library (csrc/net.cu, csrc/step.cu): same kernels, same order -- an A/B switch for debugging only.
+NATIVE = os.environ.get('GCBF_NATIVE', '1') != '0'
 ENV_IDS = {'SimpleCar': 0, 'DubinsCar': 1, 'SimpleDrone': 2}
 GEMM_IMPL = 0   # 0 auto, 1 force fp32 SIMT, 2 force tcgen05 (tests flip this)
 
@@ -36,9 +41,19 @@ class _GemmTimer:
 
     def enable(self):
         self.on, self.records, self.prep = True, [], []
+        native.fn('gcbf_timing_enable')(1)
 
     def disable(self):
         self.on, self.records, self.prep = False, [], []
+        native.fn('gcbf_timing_enable')(0)
+
+    def _collect_native(self):
+        """(ms, flops, kind, M, N, K) records of the launches the chain-level entry points made (csrc/net.cu `Timed`)."""
+        cap = 1 << 16
+        buf = (native.TimeRec * cap)()
+        cnt = ctypes.c_int(0)
+        native.check(native.fn('gcbf_timing_collect')(buf, cap, ctypes.byref(cnt)), 'gcbf_timing_collect')
+        return [(buf[i].ms, buf[i].flops, buf[i].kind, buf[i].M, buf[i].N, buf[i].K) for i in range(min(cnt.value, cap))]
 
     def run(self, flops, fn, impl=None, tag=None):
         if not self.on:
@@ -74,6 +89,21 @@ class _GemmTimer:
                 t[1] += flops
                 t[2] += 1
         prep_ms = sum(e0.elapsed_time(e1) for e0, e1 in self.prep)
+        nprep = len(self.prep)
+        for ms, flops, kind, M, N, K in self._collect_native():
+            if kind == 4:
+                prep_ms += ms
+                nprep += 1
+                continue
+            b = by[2] if kind in (0, 1, 2) else by[1]
+            b[0] += ms
+            b[1] += flops
+            b[2] += 1
+            if kind in (0, 1, 2):
+                t = shapes.setdefault((('forward', 'data-grad', 'weight-grad')[kind], M, N, K), [0.0, 0.0, 0])
+                t[0] += ms
+                t[1] += flops
+                t[2] += 1
         tensor = by[2][1] > by[1][1]
         ms, flops, n = by[2] if tensor else by[1]
         dominant = None
@@ -81,7 +111,7 @@ class _GemmTimer:
             tag, (tms, tfl, tn) = max(shapes.items(), key=lambda kv: kv[1][0])
             dominant = dict(product=tag[0], M=tag[1], N=tag[2], K=tag[3], launches=tn, ms_per_launch=tms / tn, flops_per_launch=tfl / tn)
         return dict(kernel='gemm_tcgen05_3xfp16' if tensor else 'gemm_simt_kernel', ms=ms, flops=flops, launches=n, tensor=tensor,
-                    prep_ms=prep_ms, prep_launches=len(self.prep), dominant=dominant,
+                    prep_ms=prep_ms, prep_launches=nprep, dominant=dominant,
                     other_ms=(by[1] if tensor else by[2])[0], other_flops=(by[1] if tensor else by[2])[1])
 
 
@@ -661,6 +691,50 @@ def _flatten_specs(specs: Sequence[LinearSpec]) -> List[torch.Tensor]:
     return out
 
 
+def _linear_array(layers, grads, views=None):
+    arr = (native.LinearDesc * len(layers))()
+    for l, L in enumerate(layers):
+        native.fill_linear(arr[l], L, views[l] if grads == 'tensors' else grads, GEMM_IMPL == 2)
+    return arr
+
+
+def native_mlp_forward(x, layers, save):
+    sync_gemm_impl()
+    xm, ldx = _mat(x)
+    M = int(xm.shape[0])
+    arr = _linear_array(layers, None)
+    out = torch.empty(M, layers[-1].W.shape[0], device=xm.device, dtype=torch.float32)
+    nbytes = native.fn('gcbf_mlp_forward_workspace_bytes')(arr, len(layers), M, 1 if save else 0)
+    ws = native.workspace(nbytes, xm.device)
+    mctx = native.MlpCtx() if save else None
+    rc = native.fn('gcbf_mlp_forward')(arr, len(layers), 1 if native._weights_stale(layers) else 0, ptr(xm), ldx, M, ptr(out), out.shape[1],
+                                       ptr(ws), ws.numel(), ctypes.byref(mctx) if save else None, _C.stream())
+    native.check(rc, 'gcbf_mlp_forward')
+    native._mark_fresh(layers)
+    return out, ((mctx, ws, xm, M) if save else None)
+
+
+def native_mlp_backward(layers, state, dy, need_dx):
+    mctx, ws, xm, M = state
+    sync_gemm_impl()
+    views = None
+    if SKIP_WGRAD:
+        arr = _linear_array(layers, None)
+    elif GRAD_INTO_PARAM:
+        arr = _linear_array(layers, 'param')
+    else:
+        views = _grad_views(layers, dy.device)
+        arr = _linear_array(layers, 'tensors', views)
+    dym, lddy = _mat(dy)
+    dx = torch.empty(M, layers[0].W.shape[1], device=dy.device, dtype=torch.float32) if need_dx else None
+    nbytes = native.fn('gcbf_mlp_backward_workspace_bytes')(arr, len(layers), M)
+    ws2 = native.workspace(nbytes, dy.device)
+    rc = native.fn('gcbf_mlp_backward')(arr, len(layers), ctypes.byref(mctx), ptr(dym), lddy, ptr(dx), 1 if SKIP_WGRAD else 0, ptr(ws2),
+                                        ws2.numel(), _C.stream())
+    native.check(rc, 'gcbf_mlp_backward')
+    return dx, (views if views is not None else [(None, None)] * len(layers))
+
+
 class MLPFunction(torch.autograd.Function):
     """gcbf.nn.MLP.forward.  apply(x, layers, *flat_params) where flat_params = [W0, b0, W1, b1, ...]."""
 
@@ -668,14 +742,23 @@ class MLPFunction(torch.autograd.Function):
     def forward(ctx, x, layers, *params):
         _C.require_cuda(x)
         need = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
-        y, mctx, _ = mlp_forward(x.detach(), layers, need)
-        ctx.layers, ctx.mctx = layers, mctx
+        ctx.layers = layers
         ctx.need_dx = ctx.needs_input_grad[0]
+        if NATIVE and len(layers) <= native.MAX_LAYERS:
+            y, ctx.mctx = native_mlp_forward(x.detach(), layers, need)
+            ctx.native = True
+            return y
+        ctx.native = False
+        y, mctx, _ = mlp_forward(x.detach(), layers, need)
+        ctx.mctx = mctx
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        dx, grads = mlp_backward(ctx.mctx, ctx.layers, dy, ctx.need_dx)
+        if ctx.native:
+            dx, grads = native_mlp_backward(ctx.layers, ctx.mctx, dy, ctx.need_dx)
+        else:
+            dx, grads = mlp_backward(ctx.mctx, ctx.layers, dy, ctx.need_dx)
         flat = []
         for dW, db in grads:
             flat += [dW, db]
@@ -789,6 +872,76 @@ def net_backward(spec: NetSpec, ctx, d_out, rowptr, row_index, need_d_edge_attr)
     return d_edge_attr, g_phi + g_gate + g_gamma + g_head
 
 
+def sync_gemm_impl():
+    """Tell the library which linear-layer implementation the chain-level calls may use (tests flip ops.GEMM_IMPL)."""
+    native.fn('gcbf_set_gemm_impl')(1 if (not USE_TCGEN05 or GEMM_IMPL == 1) else (2 if GEMM_IMPL == 2 else 0))
+
+
+def _grad_views(specs, device):
+    """One zeroed flat buffer with (gW, gb) views per layer: where gcbf_net_backward / gcbf_mlp_backward accumulate when the
+    gradients go back to autograd as tensors (outside GCBF.train_step)."""
+    total = sum(L.W.numel() + L.b.numel() for L in specs)
+    flat = torch.zeros(total, device=device, dtype=torch.float32)
+    views, off = [], 0
+    for L in specs:
+        nw, nb = L.W.numel(), L.b.numel()
+        views.append((flat[off:off + nw].view(L.W.shape), flat[off + nw:off + nw + nb]))
+        off += nw + nb
+    return views
+
+
+def native_net_forward(spec, x, edge_attr, edge_index, rowptr, row_index, head_extra, save):
+    """One gcbf_net_forward call.  Returns (out, state) -- state holds the library's context, the workspace it points into and
+    every tensor the context references."""
+    sync_gemm_impl()
+    specs = spec.all_layers()
+    dev = x.device
+    xc, ea, ei = x.contiguous(), edge_attr.contiguous(), edge_index.contiguous()
+    he = head_extra.contiguous() if head_extra is not None else None
+    E, Nn = int(ei.shape[1]), int(xc.shape[0])
+    R = int(row_index.numel()) if row_index is not None else Nn
+    nd = native.make_net_desc(spec, he.shape[1] if he is not None else 0, None, GEMM_IMPL == 2)
+    nd.refresh_weights = 1 if native._weights_stale(specs) else 0
+    out_dim = (spec.head or spec.gamma)[-1].W.shape[0]
+    out = torch.empty(R, out_dim, device=dev, dtype=torch.float32)
+    nbytes = native.fn('gcbf_net_forward_workspace_bytes')(ctypes.byref(nd), E, Nn, R, 1 if save else 0)
+    ws = native.workspace(nbytes, dev)
+    nctx = native.NetCtx() if save else None
+    rc = native.fn('gcbf_net_forward')(ctypes.byref(nd), ptr(xc), ptr(ea) if E else None, ptr(ei) if E else None, ptr(rowptr), E, Nn,
+                                       ptr(row_index), R, ptr(he), ptr(out), out_dim, ptr(ws), ws.numel(),
+                                       ctypes.byref(nctx) if save else None, _C.stream())
+    native.check(rc, 'gcbf_net_forward')
+    native._mark_fresh(specs)
+    state = (nctx, ws, (xc, ea, ei, rowptr, row_index, he), (E, Nn, R)) if save else None
+    return out, state
+
+
+def native_net_backward(spec, state, d_out, need_d_edge_attr):
+    nctx, ws, keep, (E, Nn, R) = state
+    sync_gemm_impl()
+    specs = spec.all_layers()
+    dev = d_out.device
+    he = keep[5]
+    views = None
+    if SKIP_WGRAD:
+        nd = native.make_net_desc(spec, he.shape[1] if he is not None else 0, None, GEMM_IMPL == 2)
+    elif GRAD_INTO_PARAM:
+        nd = native.make_net_desc(spec, he.shape[1] if he is not None else 0, 'param', GEMM_IMPL == 2)
+    else:
+        views = _grad_views(specs, dev)
+        nd = native.make_net_desc(spec, he.shape[1] if he is not None else 0, 'tensors', GEMM_IMPL == 2, grad_tensors=views)
+    d_out = d_out if d_out.stride(-1) == 1 else d_out.contiguous()
+    d_ea = torch.empty(E, spec.edge_dim, device=dev, dtype=torch.float32) if need_d_edge_attr else None
+    nbytes = native.fn('gcbf_net_backward_workspace_bytes')(ctypes.byref(nd), E, Nn, R, 1 if need_d_edge_attr else 0)
+    ws2 = native.workspace(nbytes, dev)
+    rc = native.fn('gcbf_net_backward')(ctypes.byref(nd), ctypes.byref(nctx), ptr(d_out), d_out.stride(0) if d_out.dim() == 2 else 1,
+                                        ptr(d_ea), 1 if SKIP_WGRAD else 0, ptr(ws2), ws2.numel(), _C.stream())
+    native.check(rc, 'gcbf_net_backward')
+    if views is None:
+        return d_ea, [(None, None)] * len(specs)
+    return d_ea, views
+
+
 class GNNNetFunction(torch.autograd.Function):
     """apply(x, edge_attr, edge_index, rowptr, row_index, head_extra, spec, *flat_params)."""
 
@@ -800,7 +953,8 @@ class GNNNetFunction(torch.autograd.Function):
                                       '(x is a constant type indicator, simple_car.py:132)')
         need = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
         he = head_extra.detach() if head_extra is not None else None
-        out, nctx = net_forward(spec, x.detach(), edge_attr.detach(), edge_index, rowptr, row_index, he, need)
+        fwd = native_net_forward if NATIVE else net_forward
+        out, nctx = fwd(spec, x.detach(), edge_attr.detach(), edge_index, rowptr, row_index, he, need)
         ctx.spec, ctx.nctx = spec, nctx
         ctx.rowptr, ctx.row_index = rowptr, row_index
         ctx.need_dea = ctx.needs_input_grad[1]
@@ -808,7 +962,10 @@ class GNNNetFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
-        d_ea, grads = net_backward(ctx.spec, ctx.nctx, d_out.contiguous(), ctx.rowptr, ctx.row_index, ctx.need_dea)
+        if NATIVE:
+            d_ea, grads = native_net_backward(ctx.spec, ctx.nctx, d_out, ctx.need_dea)
+        else:
+            d_ea, grads = net_backward(ctx.spec, ctx.nctx, d_out.contiguous(), ctx.rowptr, ctx.row_index, ctx.need_dea)
         flat = []
         for dW, db in grads:
             flat += [dW, db]

@@ -41,6 +41,10 @@ extern "C" {
 
 const char* gcbf_last_error(void);
 int gcbf_abi_version(void);
+/* sizeof() of ABI structure number `which` as the library was compiled (0 gcbf_env_cfg, 1 gcbf_linear_desc, 2 gcbf_net_desc,
+ * 3 gcbf_step_desc, 4 gcbf_step_batch, 5 gcbf_step_out, 6 gcbf_net_ctx, 7 gcbf_mlp_ctx, 8 gcbf_step_ctx, 9 gcbf_time_rec,
+ * 10 gcbf_sn_layer, 11 gcbf_split_desc; 0 for unknown): bindings check their mirrors against it */
+size_t gcbf_abi_struct_size(int which);
 /* 1 if the library was built with the tcgen05 (3xFP16) GEMM path compiled in, else 0 */
 int gcbf_has_tcgen05(void);
 /* which kernel the most recent gcbf_linear_* call on this thread launched: 1 = fp32 SIMT tile GEMM,
@@ -266,6 +270,124 @@ int gcbf_sn_grad_fixup(float* dW, int lddw, const float* W, int ldw, int N, int 
 int gcbf_grad_sumsq(const float* g, int64_t count, double* sumsq, void* stream);
 int gcbf_clip_adam(float* p, const float* g, float* m, float* v, int64_t count, const double* sumsq,
                    double max_norm, double lr, double beta1, double beta2, double eps, int step, void* stream);
+
+
+/* ===================================================================================================
+ * Chain-level entry points (ABI v3): ONE call per GNN pass / per phase of the train step instead of one per kernel.
+ * The host-side sequencing that gcbf/nn/gnn.py:27-36, gcbf/nn/mlp.py:44-47 and gcbf/algo/gcbf.py:158-226 do with ~250 ATen
+ * calls per forward lives in the library (csrc/net.cu, csrc/step.cu); the caller still owns every byte: it passes ONE
+ * workspace per call (size from the matching *_workspace_bytes query), the library bump-allocates activations, companions
+ * and gradients inside it and never allocates device memory itself.
+ * =================================================================================================== */
+#define GCBF_E_WORKSPACE (-4) /* workspace too small: the needed size is returned through the call's out-parameter */
+
+/* one nn.Linear of a gcbf.nn.MLP (gcbf/nn/mlp.py:17-41) */
+typedef struct gcbf_linear_desc {
+  const float* W; const float* b;   /* weight [N, K] (weight_orig when spectral-normalised), pitch ldw; bias [N] */
+  float* u; float* v;               /* spectral-norm buffers weight_u [N], weight_v [K] (updated in place by every forward) or NULL */
+  float* gW; float* gb;             /* where the backward ACCUMULATES dL/dW (pitch ldgw) and dL/db; NULL = no weight gradient */
+  void* Wh; void* w_amax;           /* persistent fp16 [hi|lo] companion of W (2*N*ldwh halves) + its amax word; NULL = never on tensor cores */
+  int32_t ldw, ldgw, ldwh;
+  int32_t N, K, act;                /* out-features, in-features, GCBF_ACT_* applied to this layer's output */
+} gcbf_linear_desc;
+
+#define GCBF_MAX_MLP_LAYERS 4
+/* CBFGNNLayer / ControllerGNNLayer (gcbf/nn/gnn.py:14-36, 56-73) + optional row selection + head MLP
+ * (CBFGNN.forward gcbf/algo/gcbf.py:37-55, GNNController.forward gcbf/controller/gnn_controller.py:29-48) */
+typedef struct gcbf_net_desc {
+  gcbf_linear_desc phi[GCBF_MAX_MLP_LAYERS], gate[GCBF_MAX_MLP_LAYERS], gamma[GCBF_MAX_MLP_LAYERS], head[GCBF_MAX_MLP_LAYERS];
+  int32_t n_phi, n_gate, n_gamma, n_head;   /* n_head == 0: the pass ends with gamma's output */
+  int32_t node_dim, edge_dim, phi_dim;
+  int32_t head_extra_dim;                   /* columns concatenated to gamma's output before the head (u_ref: action_dim), or 0 */
+  int32_t refresh_weights;                  /* != 0: the weights changed since the companions were made -> re-split them first */
+  int32_t pad_;
+} gcbf_net_desc;
+
+/* what a forward saves for its backward: pointers into the forward's workspace (which must stay alive and untouched) */
+typedef struct gcbf_net_ctx { uint64_t opaque[160]; } gcbf_net_ctx;
+
+/* bytes a forward (save_ctx != 0: everything the backward reads is kept) / a backward needs for E edges, num_nodes nodes,
+ * `rows` gamma rows (= num_nodes without row selection) */
+size_t gcbf_net_forward_workspace_bytes(const gcbf_net_desc* net, int64_t num_edges, int num_nodes, int rows, int save_ctx);
+size_t gcbf_net_backward_workspace_bytes(const gcbf_net_desc* net, int64_t num_edges, int num_nodes, int rows, int need_d_edge_attr);
+/* out[rows, out_dim] (pitch ld_out) = head(gamma(cat[aggr, x])[row_index] ++ head_extra); row_index (int64[rows]) NULL = all nodes.
+ * ctx NULL = inference (nothing kept).  Advances the spectral-norm buffers by one power iteration (the reference never calls
+ * .eval()). */
+int gcbf_net_forward(const gcbf_net_desc* net, const float* x, const float* edge_attr, const int64_t* edge_index,
+                     const int32_t* rowptr, int64_t num_edges, int num_nodes, const int64_t* row_index, int rows,
+                     const float* head_extra, float* out, int ld_out, void* workspace, size_t workspace_bytes,
+                     gcbf_net_ctx* ctx, void* stream);
+/* accumulates weight / bias gradients into the descriptors' gW / gb (skipped where NULL or when skip_wgrad != 0) and writes
+ * d_edge_attr [E, edge_dim] if it is not NULL */
+int gcbf_net_backward(const gcbf_net_desc* net, const gcbf_net_ctx* ctx, const float* d_out, int ld_dout, float* d_edge_attr,
+                      int skip_wgrad, void* workspace, size_t workspace_bytes, void* stream);
+/* a bare MLP (gcbf.nn.MLP.forward, mlp.py:44-47) through the same chain code */
+typedef struct gcbf_mlp_ctx { uint64_t opaque[48]; } gcbf_mlp_ctx;
+size_t gcbf_mlp_forward_workspace_bytes(const gcbf_linear_desc* layers, int n_layers, int rows, int save_ctx);
+size_t gcbf_mlp_backward_workspace_bytes(const gcbf_linear_desc* layers, int n_layers, int rows);
+int gcbf_mlp_forward(const gcbf_linear_desc* layers, int n_layers, int refresh_weights, const float* x, int ldx, int rows,
+                     float* out, int ld_out, void* workspace, size_t workspace_bytes, gcbf_mlp_ctx* ctx, void* stream);
+int gcbf_mlp_backward(const gcbf_linear_desc* layers, int n_layers, const gcbf_mlp_ctx* ctx, const float* d_out, int ld_dout,
+                      float* d_x /* [rows, K0] or NULL */, int skip_wgrad, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One inner iteration of GCBF.update (gcbf/algo/gcbf.py:158-226) in three calls, so that data-parallel callers can put
+ * their two collectives in between (loss partial sums after `relink`, gradient bucket after `backward`):
+ *   gcbf_step_forward : h = cbf(graphs), actions = actor(graphs) (side stream), masks, forward_graph, h_next = cbf(graphs_next);
+ *                       starts the re-linked radius graph on the side stream
+ *   gcbf_step_relink  : waits for the re-linked edge count (the step's ONE host sync), h_next_new = cbf(re-linked graphs),
+ *                       loss partial sums -> partial[16]; returns GCBF_E_WORKSPACE (+ *needed_bytes) BEFORE launching anything
+ *                       if workspace2 is too small for the re-linked graph -- call again with a larger one
+ *   gcbf_step_backward: loss gradients from the (all-reduced) partials, the three backward passes, scalars[8]
+ * All device results live in the caller's workspaces; `out` reports where. */
+typedef struct gcbf_step_desc {
+  gcbf_net_desc cbf, actor;
+  gcbf_env_cfg env;
+  const float* goal; const float* lqr_gain;     /* goal [num_agents, ld_goal]; LQR gain or NULL (DubinsCar) */
+  int32_t ld_goal, state_dim, pos_dim, action_dim;
+  int32_t graph_metric;                          /* K1 metric: 0 SimpleCar, 1 DubinsCar / SimpleDrone */
+  float comm_radius;
+  float alpha, eps, coef_unsafe, coef_safe, coef_hdot, coef_action;
+  float* grad_bucket; int64_t grad_bucket_floats;   /* zeroed by gcbf_step_backward before the gradients accumulate (NULL: caller zeroes) */
+} gcbf_step_desc;
+
+typedef struct gcbf_step_batch {
+  const float* states; int32_t ld_state;       /* [B*N, state_dim] */
+  const float* x;                              /* [B*N, node_dim] */
+  const float* edge_attr;                      /* [E, edge_dim] */
+  const int64_t* edge_index;                   /* [2, E] target-sorted */
+  const int32_t* rowptr;                       /* CSR over all B*N nodes */
+  const float* u_ref;                          /* [B*n, action_dim] (the STORED nominal control, gnn_controller.py:46) */
+  const int64_t* row_index;                    /* agent rows (nonzero(agent_mask)) or NULL when every node is an agent */
+  int64_t num_edges; int32_t num_nodes; int32_t num_agents_total;
+} gcbf_step_batch;
+
+typedef struct gcbf_step_out {   /* device pointers into the workspaces, valid until the workspaces are reused */
+  float* h; float* actions; float* h_next; float* h_next_new; float* hdot; float* scalars;   /* [M,1] [M,a] [M,1] [M] [M] [8] */
+  uint8_t* safe; uint8_t* unsafe;                                                        /* [M] each */
+  double* partial;                                                                       /* [16] */
+  int64_t* edge_index_new; int64_t num_edges_new;                                        /* re-linked graph [2, E'] */
+} gcbf_step_out;
+
+typedef struct gcbf_step_ctx { uint64_t opaque[640]; } gcbf_step_ctx;
+
+size_t gcbf_step_workspace_bytes(const gcbf_step_desc* d, const gcbf_step_batch* b);            /* workspace (forward + backward) */
+size_t gcbf_step_relink_workspace_bytes(const gcbf_step_desc* d, const gcbf_step_batch* b, int64_t num_edges_new);
+int gcbf_step_forward(const gcbf_step_desc* d, const gcbf_step_batch* b, void* workspace, size_t workspace_bytes,
+                      gcbf_step_ctx* ctx, gcbf_step_out* out, void* stream, void* side_stream /* NULL: single stream */);
+int gcbf_step_relink(const gcbf_step_desc* d, const gcbf_step_batch* b, gcbf_step_ctx* ctx, void* workspace2,
+                     size_t workspace2_bytes, size_t* needed_bytes, gcbf_step_out* out, void* stream, void* side_stream);
+int gcbf_step_backward(const gcbf_step_desc* d, const gcbf_step_batch* b, gcbf_step_ctx* ctx, gcbf_step_out* out, void* stream,
+                       void* side_stream);
+
+/* instrumentation (bench.py): kernels launched by the chain-level calls since the last reset, and optional CUDA-event timing of
+ * every linear-layer launch (kind 0 forward / 1 data-grad / 2 weight-grad on the tensor cores, 3 fp32 linear kernels, 4 operand
+ * preparation = amax + fp16 split) */
+long long gcbf_launch_count(int reset);
+typedef struct gcbf_time_rec { double ms; double flops; int32_t kind; int32_t M, N, K; } gcbf_time_rec;
+int gcbf_timing_enable(int on);
+int gcbf_timing_collect(gcbf_time_rec* out, int max_records, int* count);   /* synchronises the device; clears the records */
+/* 0 auto, 1 force the fp32 SIMT kernels, 2 force the tensor-core path (tests) -- what gcbf_b200.ops.GEMM_IMPL was */
+int gcbf_set_gemm_impl(int impl);
 
 #ifdef __cplusplus
 }

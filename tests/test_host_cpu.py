@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from conftest import ROOT
-from gcbf_b200 import _C
+from gcbf_b200 import _C, native   # noqa: F401  (native registers the chain-level entry points)
 from gcbf_b200.data import Batch, Data
 
 
@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/gcbf_b200.h but not exported'
     assert sorted(_C.EXPORTED_SYMBOLS) == declared, set(_C.EXPORTED_SYMBOLS) ^ set(declared)
-    assert _C.lib().gcbf_abi_version() == 2
+    assert _C.lib().gcbf_abi_version() == 3
 
 
 def test_env_cfg_struct_layout():
@@ -209,7 +209,7 @@ def test_tensor_core_dispatch_rule():
     finally:
         ops.GEMM_IMPL = old
     # the host rule is the library's rule
-    from gcbf_b200 import _C
+    from gcbf_b200 import _C, native   # noqa: F401  (native registers the chain-level entry points)
     lib = _C.lib()
     for M in (1, 255, 256, 4531, 24196):
         for N in (1, 32, 95, 96, 128, 2048):
@@ -359,3 +359,38 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     assert lib.gcbf_sn_power_iter_batched(None, 1, ok_ptr, 0, None) == -1
     # the fp32 entry points keep their "tensor-core path has its own entry point" answer for impl = 2
     assert lib.gcbf_linear_fwd(ok_ptr, 64, ok_ptr, 64, None, None, ok_ptr, 64, 0, 64, 64, 0, 2, None, None) in (0, -3)
+
+
+def test_abi_struct_mirrors_and_workspace_queries_without_a_gpu():
+    """The ctypes mirrors of the chain-level ABI structures have the library's sizes, and the workspace queries (which replay a
+    call's allocation sequence without launching) work on descriptors built from CPU tensors: sizes grow with the edge count and a
+    whole C3 step (~206 k edges, 65,536 agents) fits one B200 (180 GB) with room to spare."""
+    from gcbf_b200 import synth
+    from gcbf_b200.synth import seeded_algo
+    mirrors = [_C.EnvCfg, native.LinearDesc, native.NetDesc, native.StepDesc, native.StepBatch, native.StepOut, native.NetCtx,
+               native.MlpCtx, native.StepCtx, native.TimeRec, _C.SnLayer, _C.SplitDesc]
+    for i, m in enumerate(mirrors):
+        assert ctypes.sizeof(m) == _C.lib().gcbf_abi_struct_size(i), m.__name__
+    assert _C.lib().gcbf_abi_struct_size(99) == 0
+    sizes = {}
+    for cfg, E in (('C2', 24196), ('C3', 206139)):
+        c = dict(synth.CONFIGS[cfg])
+        sb = synth.make_states(c['env'], c['num_agents'], c['num_obs'], 1, c['area_size'], 1)
+        env, algo = seeded_algo(sb.env, sb.num_agents, torch.device('cpu'), 0, {'num_obs': sb.num_obs, 'area_size': sb.area_size})
+        env.set_goal(sb.goals)
+        d = algo._step_desc()[0]
+        B = c['num_graphs']
+        cfg_s = env._cfg(B)
+        ctypes.memmove(ctypes.byref(d.env), ctypes.byref(cfg_s), ctypes.sizeof(_C.EnvCfg))
+        b = native.StepBatch()
+        fake = 1 << 20
+        b.states, b.ld_state, b.x, b.edge_attr, b.edge_index, b.rowptr, b.u_ref = fake, env.state_dim, fake, fake, fake, fake, fake
+        b.row_index = fake if sb.num_obs else None
+        b.num_edges, b.num_nodes, b.num_agents_total = E, B * sb.nodes_per_graph, B * sb.num_agents
+        need = native.fn('gcbf_step_workspace_bytes')(ctypes.byref(d), ctypes.byref(b))
+        relink = native.fn('gcbf_step_relink_workspace_bytes')(ctypes.byref(d), ctypes.byref(b), E)
+        assert need > 0 and relink > 0, _C.lib().gcbf_last_error()
+        sizes[cfg] = (need, relink)
+        b.num_agents_total += 1                                   # inconsistent batch: rejected, not a crash
+        assert native.fn('gcbf_step_workspace_bytes')(ctypes.byref(d), ctypes.byref(b)) == 0
+    assert sizes['C2'][0] < sizes['C3'][0] < 80e9 and sizes['C3'][1] < 20e9

@@ -23,8 +23,9 @@ def run(M, N, K, impl, scale_x=1.0, scale_dz=1.0):
     return e(y, ry), e(dx, rdx), e(dW, rdW), e(db, dz64.sum(0))
 
 
-for shape in [(256, 256, 96), (384, 128, 96), (1000, 2048, 2048), (2500, 256, 2048), (777, 2048, 260), (4096, 512, 1024),
-              (300, 130, 100), (70000, 128, 256)]:
+ACC_SHAPES = [] if os.environ.get('GEMM_CHECK_TIMING_ONLY') else [(256, 256, 96), (384, 128, 96), (1000, 2048, 2048), (2500, 256, 2048), (777, 2048, 260),
+                                                                  (4096, 512, 1024), (300, 130, 100), (70000, 128, 256)]
+for shape in ACC_SHAPES:
     for sx, sdz in [(1.0, 1.0), (1e-3, 1e-7)]:
         try:
             r2 = run(*shape, 2, sx, sdz)
@@ -45,6 +46,9 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
+print('GCBF_TC_KCH =', os.environ.get('GCBF_TC_KCH', 'default (4)'))
+for shape in [(1000, 2048, 2048), (70000, 128, 256)]:
+    print(shape, 'tcgen05 err y/dx/dW/db vs fp64: %.2e %.2e %.2e %.2e' % run(*shape, 2), flush=True)
 # timing at the real layer size (C2: E = 24,196 edges, 2048 x 2048 layer)
 ops.GEMM_IMPL = 0
 for (M, N, K) in [(24196, 2048, 2048), (8192, 2048, 2048), (24196, 256, 2048), (206139, 2048, 2048)]:
