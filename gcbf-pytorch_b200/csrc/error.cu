@@ -17,7 +17,7 @@ extern "C" int gcbf_abi_version(void) { return 3; }   // 2: fp16-companion tenso
 
 // sizeof() of the ABI structures as this library was compiled (bindings check their mirrors against it):
 // 0 gcbf_env_cfg, 1 gcbf_linear_desc, 2 gcbf_net_desc, 3 gcbf_step_desc, 4 gcbf_step_batch, 5 gcbf_step_out, 6 gcbf_net_ctx,
-// 7 gcbf_mlp_ctx, 8 gcbf_step_ctx, 9 gcbf_time_rec, 10 gcbf_sn_layer, 11 gcbf_split_desc
+// 7 gcbf_mlp_ctx, 8 gcbf_step_ctx, 9 gcbf_time_rec, 10 gcbf_sn_layer, 11 gcbf_split_desc, 12 gcbf_h16
 extern "C" size_t gcbf_abi_struct_size(int which) {
   switch (which) {
     case 0: return sizeof(gcbf_env_cfg);
@@ -32,6 +32,7 @@ extern "C" size_t gcbf_abi_struct_size(int which) {
     case 9: return sizeof(gcbf_time_rec);
     case 10: return sizeof(gcbf_sn_layer);
     case 11: return sizeof(gcbf_split_desc);
+    case 12: return sizeof(gcbf_h16);
     default: return 0;
   }
 }

@@ -43,6 +43,7 @@ constexpr int BK = GCBF_TH_BK;         // K elements per k-block (= one smem sta
 static_assert(BK == 32 || BK == 64, "BK must be 32 or 64");
 constexpr int UMMA_K = 16;             // fp16: 32 bytes of K per instruction
 constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 promotion / epilogue
+constexpr int EPI_WARP0 = 2;
 constexpr int KCH_MAX = 256 / BK;      // k-blocks accumulated inside the tensor core before promotion to registers: upper limit (256 K-elements)
 constexpr int MN_BOX = 64;             // MN-major operands: one TMA box = 64 MN elements (128 B, SWIZZLE_128B) x BK k-rows
 
@@ -53,14 +54,25 @@ struct EpiParams {
   const float* alpha;          // device scalar (1/sigma of the spectral norm) or null
   const float* bias;
   int act;
-  const float* relu_src;
+  const float* relu_src;       // data-grad: ReLU mask source as fp32 (mask = src > 0) ...
   int ld_relu;
+  const __half* relu_hi;       // ... or as the hi plane of the layer output's companion (mask = hi > 0)
+  int ld_relu_h;
   int accumulate;
   int atomic;
-  const uint32_t* amax_a;      // device: float bits of max|A|, max|B| (the scales the companions were made with)
-  const uint32_t* amax_b;
+  // amax words of the operands' companions: one per tensor (strides 0) or one per (128-row, 256-column) tile of the operand's own
+  // matrix (strides in words: *_sr per row block, *_sc per column tile)
+  const uint32_t* amax_a; int a_sr, a_sc;
+  const uint32_t* amax_b; int b_sr, b_sc;
   uint32_t* amax_out;          // optional: atomicMax of |output| (feeds the next layer's split), or null
-  int tma_store;               // output tile leaves through shared memory + cp.async.bulk.tensor stores (plain overwrite only)
+  int tma_store;               // fp32 output tile leaves through shared memory + cp.async.bulk.tensor stores (plain overwrite only)
+  int write_f32;               // 0: no fp32 output at all (the companion is the only product)
+  // tile-scaled fp16 [hi|lo] companion of the OUTPUT, written by the epilogue (BN == 256 only): every CTA knows the exact max of its
+  // 128 x 256 tile, so the scale needs neither a pass over the tensor nor an a-priori bound
+  int emit_h;
+  uint32_t* out_tile_amax;     // [ceil(Mo/128)][out_amax_stride] float bits of the tile maxima
+  int out_amax_stride;
+  float* colsum;               // optional: column sums of the (masked) output are atomically added here (bias gradient = colsum of dZ)
   int dbg;                     // GCBF_TC_DBG experiments: 1 = skip the global stores of the epilogue, 2 = no TMA stores
 };
 
@@ -118,7 +130,8 @@ template <int BN, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-              const __grid_constant__ CUtensorMap map_c, float* __restrict__ C, int ldc, int Mo, int No, int tiles_m, int tiles_n, int kblocks_per_split, int kblocks_total, int KCH, EpiParams ep) {
+              const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_oh,
+              const __grid_constant__ CUtensorMap map_ol, float* __restrict__ C, int ldc, int Mo, int No, int tiles_m, int tiles_n, int kblocks_per_split, int kblocks_total, int KCH, EpiParams ep) {
   using K = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,6 +142,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   uint64_t* tfull = bars + 2 * K::STAGES;       // [2]       MMA -> epilogue
   uint64_t* tempty = bars + 2 * K::STAGES + 2;  // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * K::STAGES + 4);
+  uint32_t* epi_red = tmem_slot + 2;            // [2][8] per-warp maxima of the current output tile (double-buffered across tiles)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb0 = blockIdx.y * kblocks_per_split;
@@ -146,6 +160,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     tma_prefetch_desc(&map_b_hi);
     tma_prefetch_desc(&map_b_lo);
     if (ep.tma_store) tma_prefetch_desc(&map_c);
+    if (ep.emit_h) { tma_prefetch_desc(&map_oh); tma_prefetch_desc(&map_ol); }
     for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * CG); }   // one arrive per epilogue warp (of both CTAs)
     fence_barrier_init();
@@ -223,16 +238,17 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           }
         }
       }
-    } else {
+    } else if (warp >= EPI_WARP0) {
       // ===== promotion / epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
       constexpr int CH = BN / 2;                               // columns owned by one thread
+      constexpr int MODE = A_MN ? EPI_WGRAD : (B_MN ? EPI_DGRAD : EPI_FWD);   // the operand layouts identify the product
       const int lg = warp & 3;
-      const int chalf = (warp - 2) >> 2;
-      const uint32_t sa = scale_bits_from_amax(__ldg(ep.amax_a)), sb = scale_bits_from_amax(__ldg(ep.amax_b));
-      const float alpha = (ep.alpha ? __ldg(ep.alpha) : 1.f) * __uint_as_float(inv_pow2_bits(sa)) * __uint_as_float(inv_pow2_bits(sb));
+      const int chalf = (warp - EPI_WARP0) >> 2;
+      const float alpha = ep.alpha ? __ldg(ep.alpha) : 1.f;
       int buf = 0;
       uint32_t tphase[2] = {0, 0};
       float out_max = 0.f;
+      int tile_par = 0;
       for (int t = tile0; t < num_tiles; t += tile_stride) {
         const int m0 = (t / tiles_n) * (BM * CG) + rank * BM, n0 = (t % tiles_n) * BN;
         float acc[CH];
@@ -240,7 +256,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         for (int j = 0; j < CH; ++j) acc[j] = 0.f;
         const int nch = (nkb + KCH - 1) / KCH;
         for (int c = 0; c < nch; ++c) {
-          // add the finished chunk sum of TMEM buffer `buf` into the register accumulators (round-to-nearest fp32)
+          // descale factor of this chunk: 1 / (s_a * s_b), powers of two.  Per-tensor companions: the same word every chunk;
+          // tile-scaled companions: the word of the (128-row, 256-column) tile of the operand this chunk's k-range lies in
+          const int kstart = (kb0 + c * KCH) * BK;
+          const int ia = A_MN ? (kstart >> 7) * ep.a_sr + (m0 >> 8) * ep.a_sc : (m0 >> 7) * ep.a_sr + (kstart >> 8) * ep.a_sc;
+          const int ib = B_MN ? (kstart >> 7) * ep.b_sr + (n0 >> 8) * ep.b_sc : 0;
+          const float cs = __uint_as_float(inv_pow2_bits(scale_bits_from_amax(__ldg(ep.amax_a + ia)))) *
+                           __uint_as_float(inv_pow2_bits(scale_bits_from_amax(__ldg(ep.amax_b + ib))));
+          // add the finished chunk sum of TMEM buffer `buf` into the register accumulators (one round-to-nearest fp32 FMA each)
           mbar_wait(&tfull[buf], tphase[buf]);
           tcgen05_fence_after();
           const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + chalf * CH) + ((uint32_t)(lg * 32) << 16);
@@ -250,7 +273,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             tmem_ld_32x32b_x32(taddr + (uint32_t)(cc * 32), r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[cc * 32 + j] = __fadd_rn(acc[cc * 32 + j], __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) acc[cc * 32 + j] = __fmaf_rn(__uint_as_float(r[j]), cs, acc[cc * 32 + j]);
           }
           tcgen05_fence_before();
           __syncwarp();
@@ -260,99 +283,229 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
         const int row = m0 + lg * 32 + lane;
         const bool row_ok = row < Mo;
-        const uint32_t my_stage = smem_u32(out_stage + (warp - 2) * 4096);
+        const uint32_t my_stage = smem_u32(out_stage + (warp - EPI_WARP0) * 4096);
+        const bool need_clean = ep.emit_h || ep.colsum || ep.amax_out;     // out-of-range entries must read as exact zeros
+        // ---- pass 1: finish the values in place: alpha, bias, activation / ReLU mask
+        float tmax = 0.f;
 #pragma unroll
         for (int c = 0; c < CH / 32; ++c) {
           const int col0 = n0 + chalf * CH + c * 32;
-          if (col0 >= No) continue;                            // warp-uniform
-          float* dst = C + (size_t)row * ldc + col0;
-          const int nv = min(32, No - col0);
-          float v[32];
+          if (col0 >= No) {                                    // warp-uniform
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = alpha * acc[c * 32 + j];
+            for (int j = 0; j < 32; ++j) acc[c * 32 + j] = 0.f;
+            continue;
+          }
+          const int nv = min(32, No - col0);
           const bool full32 = (nv == 32);
-          if (ep.mode == EPI_FWD) {
-            float bv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] *= alpha;
+          if constexpr (MODE == EPI_FWD) {
             if (ep.bias && full32 && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-                bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+                acc[c * 32 + j] += b4.x; acc[c * 32 + j + 1] += b4.y; acc[c * 32 + j + 2] += b4.z; acc[c * 32 + j + 3] += b4.w;
               }
-            } else {
+            } else if (ep.bias) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) bv[j] = (ep.bias && j < nv) ? __ldg(ep.bias + col0 + j) : 0.f;
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) acc[c * 32 + j] += __ldg(ep.bias + col0 + j);
             }
+            if (ep.act == GCBF_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float y = v[j] + bv[j];
-              if (ep.act == GCBF_ACT_RELU) y = fmaxf(y, 0.f);
-              else if (ep.act == GCBF_ACT_TANH) y = tanhf(y);
-              v[j] = y;
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = fmaxf(acc[c * 32 + j], 0.f);
+            } else if (ep.act == GCBF_ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[c * 32 + j] = tanhf(acc[c * 32 + j]);
             }
-          } else if (ep.mode == EPI_DGRAD && ep.relu_src && row_ok) {
+          }
+          if constexpr (MODE == EPI_DGRAD) {
+          if (ep.relu_src && row_ok) {
             const float* ms = ep.relu_src + (size_t)row * ep.ld_relu + col0;
             if (full32 && ((reinterpret_cast<uintptr_t>(ms) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 m4 = __ldg(reinterpret_cast<const float4*>(ms + j));
-                v[j] = m4.x > 0.f ? v[j] : 0.f; v[j + 1] = m4.y > 0.f ? v[j + 1] : 0.f;
-                v[j + 2] = m4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = m4.w > 0.f ? v[j + 3] : 0.f;
+                acc[c * 32 + j] = m4.x > 0.f ? acc[c * 32 + j] : 0.f; acc[c * 32 + j + 1] = m4.y > 0.f ? acc[c * 32 + j + 1] : 0.f;
+                acc[c * 32 + j + 2] = m4.z > 0.f ? acc[c * 32 + j + 2] : 0.f; acc[c * 32 + j + 3] = m4.w > 0.f ? acc[c * 32 + j + 3] : 0.f;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < nv) v[j] = (__ldg(ms + j) > 0.f) ? v[j] : 0.f;
+                if (j < nv) acc[c * 32 + j] = (__ldg(ms + j) > 0.f) ? acc[c * 32 + j] : 0.f;
             }
-          }
-          if (ep.dbg & 1) {
-            if (v[0] == 123.456f && row_ok) dst[0] = v[1];
-          } else if (ep.tma_store) {
-            // the 32 x 32 chunk leaves through this warp's shared-memory stage as ONE bulk tensor store: full 128-byte rows,
-            // asynchronous (the warp does not wait on the memory system), ragged edges clipped by the tensor map
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous chunk has left the stage
-            __syncwarp();
-            const uint32_t rbase = my_stage + (uint32_t)(lane * 128);
+          } else if (ep.relu_hi && row_ok) {
+            // mask from the hi plane of the layer output's companion: y > 0  <=>  fp16(y * s) > 0 (up to y < 2^-40 of the tile max)
+            const __half* ms = ep.relu_hi + (size_t)row * ep.ld_relu_h + col0;
+            if (full32 && ((reinterpret_cast<uintptr_t>(ms) & 15) == 0)) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (uint32_t)(((q ^ (lane & 7)) << 4))), "f"(v[4 * q]),
-                           "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
-                           : "memory");
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                               reinterpret_cast<uint64_t>(&map_c)),
-                           "r"(my_stage), "r"(col0), "r"(m0 + lg * 32)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-          } else if (row_ok) {
-            if (ep.mode == EPI_WGRAD && ep.atomic) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) atomicAdd(dst + j, v[j]);
-            } else if (ep.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) { v[j] += dst[j]; dst[j] = v[j]; }
-            } else if (nv == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int q = 0; q < 4; ++q) {
+                const uint4 m8 = __ldg(reinterpret_cast<const uint4*>(ms) + q);
+                // positive fp16 (sign 0, non-zero) = bit patterns 0x0001..0x7fff
+                acc[c * 32 + q * 8 + 0] = ((m8.x & 0xffffu) - 1u < 0x7fffu) ? acc[c * 32 + q * 8 + 0] : 0.f;
+                acc[c * 32 + q * 8 + 1] = ((m8.x >> 16) - 1u < 0x7fffu) ? acc[c * 32 + q * 8 + 1] : 0.f;
+                acc[c * 32 + q * 8 + 2] = ((m8.y & 0xffffu) - 1u < 0x7fffu) ? acc[c * 32 + q * 8 + 2] : 0.f;
+                acc[c * 32 + q * 8 + 3] = ((m8.y >> 16) - 1u < 0x7fffu) ? acc[c * 32 + q * 8 + 3] : 0.f;
+                acc[c * 32 + q * 8 + 4] = ((m8.z & 0xffffu) - 1u < 0x7fffu) ? acc[c * 32 + q * 8 + 4] : 0.f;
+                acc[c * 32 + q * 8 + 5] = ((m8.z >> 16) - 1u < 0x7fffu) ? acc[c * 32 + q * 8 + 5] : 0.f;
+                acc[c * 32 + q * 8 + 6] = ((m8.w & 0xffffu) - 1u < 0x7fffu) ? acc[c * 32 + q * 8 + 6] : 0.f;
+                acc[c * 32 + q * 8 + 7] = ((m8.w >> 16) - 1u < 0x7fffu) ? acc[c * 32 + q * 8 + 7] : 0.f;
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < nv) dst[j] = v[j];
+                if (j < nv) acc[c * 32 + j] = (__half2float(ms[j]) > 0.f) ? acc[c * 32 + j] : 0.f;
             }
           }
-          if (ep.amax_out && row_ok) {
+          }
+          if (need_clean) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nv) out_max = fmaxf(out_max, fabsf(v[j]));
+            for (int j = 0; j < 32; ++j) {
+              if (!row_ok || j >= nv) acc[c * 32 + j] = 0.f;
+              tmax = fmaxf(tmax, fabsf(acc[c * 32 + j]));
+            }
+          }
+        }
+        // ---- tile maximum (companion scale): 8 warps of this CTA own the 128 x BN tile
+        float s_tile = 1.f, inv_s_tile = 1.f;
+        if (MODE != EPI_WGRAD && ep.emit_h) {
+          const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(tmax));   // non-negative floats order like uints
+          if (lane == 0) epi_red[tile_par * 8 + (warp - EPI_WARP0)] = wmax;
+          asm volatile("bar.sync 1, 256;" ::: "memory");                                 // the 8 epilogue warps only
+          uint32_t m = 0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) m = max(m, epi_red[tile_par * 8 + w]);
+          tile_par ^= 1;
+          s_tile = __uint_as_float(scale_bits_from_amax(m));
+          inv_s_tile = __uint_as_float(inv_pow2_bits(scale_bits_from_amax(m)));
+          if (warp == EPI_WARP0 && lane == 0 && m0 < Mo && n0 < No) ep.out_tile_amax[(size_t)(m0 >> 7) * ep.out_amax_stride + (n0 >> 8)] = m;
+        }
+        // ---- pass 2: outputs
+        if (ep.write_f32) {
+#pragma unroll
+          for (int c = 0; c < CH / 32; ++c) {
+            const int col0 = n0 + chalf * CH + c * 32;
+            if (col0 >= No) continue;                            // warp-uniform
+            float* dst = C + (size_t)row * ldc + col0;
+            const int nv = min(32, No - col0);
+            if (ep.dbg & 1) {
+              if (acc[c * 32 + 0] == 123.456f && row_ok) dst[0] = acc[c * 32 + 1];
+            } else if (ep.tma_store) {
+              // the 32 x 32 chunk leaves through this warp's shared-memory stage as ONE bulk tensor store: full 128-byte rows,
+              // asynchronous (the warp does not wait on the memory system), ragged edges clipped by the tensor map
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous chunk has left the stage
+              __syncwarp();
+              const uint32_t rbase = my_stage + (uint32_t)(lane * 128);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (uint32_t)(((q ^ (lane & 7)) << 4))), "f"(acc[c * 32 + 4 * q]),
+                             "f"(acc[c * 32 + 4 * q + 1]), "f"(acc[c * 32 + 4 * q + 2]), "f"(acc[c * 32 + 4 * q + 3])
+                             : "memory");
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                 reinterpret_cast<uint64_t>(&map_c)),
+                             "r"(my_stage), "r"(col0), "r"(m0 + lg * 32)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            } else if (row_ok) {
+              if (MODE == EPI_WGRAD && ep.atomic) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) atomicAdd(dst + j, acc[c * 32 + j]);
+              } else if (ep.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) { const float o = acc[c * 32 + j] + dst[j]; dst[j] = o; if (ep.amax_out) out_max = fmaxf(out_max, fabsf(o)); }
+              } else if (nv == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[c * 32 + j], acc[c * 32 + j + 1], acc[c * 32 + j + 2], acc[c * 32 + j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) dst[j] = acc[c * 32 + j];
+              }
+            }
+          }
+        }
+        if (ep.amax_out && !ep.accumulate) out_max = fmaxf(out_max, tmax);
+        if (MODE != EPI_WGRAD && ep.emit_h) {
+          // the companion of this warp's 32 x CH block: per 64-column group one 32 x 64 fp16 box per plane (128-byte rows) through
+          // the warp's shared-memory stage and a bulk tensor store; hi = fp16(y s), lo = fp16(y s - hi) as in split_h4_kernel
+          if constexpr (CH >= 64) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) acc[j] *= s_tile;       // exact (power of two); the column sums below are descaled again
+#pragma unroll
+            for (int g = 0; g < CH / 64; ++g) {
+              const int col0 = n0 + chalf * CH + g * 64;
+              if (col0 >= No) continue;                          // warp-uniform
+#pragma unroll 1
+              for (int plane = 0; plane < 2; ++plane) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                const uint32_t rbase = my_stage + (uint32_t)(lane * 128);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {                  // 16-byte unit q of this lane's 128-byte row = columns 8q .. 8q+7
+                  uint32_t w[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float y0 = acc[g * 64 + 8 * q + 2 * u], y1 = acc[g * 64 + 8 * q + 2 * u + 1];
+                    __half2 h = __floats2half2_rn(y0, y1);
+                    if (plane) {
+                      const float2 hf = __half22float2(h);
+                      h = __floats2half2_rn(__fsub_rn(y0, hf.x), __fsub_rn(y1, hf.y));
+                    }
+                    w[u] = *reinterpret_cast<const uint32_t*>(&h);
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (uint32_t)(((q ^ (lane & 7)) << 4))), "r"(w[0]), "r"(w[1]),
+                               "r"(w[2]), "r"(w[3])
+                               : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                   reinterpret_cast<uint64_t>(plane ? &map_ol : &map_oh)),
+                               "r"(my_stage), "r"(col0), "r"(m0 + lg * 32)
+                               : "memory");
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+              }
+            }
+          }
+        }
+        if (MODE == EPI_DGRAD && ep.colsum) {
+          // column sums over this warp's 32 rows (the bias gradient of the layer below = colsum of dZ): each 32 x 32 chunk goes
+          // through the warp's shared-memory stage (same swizzled layout as the fp32 output boxes), lane j adds up column j, one
+          // atomic per column per warp.  (A shuffle butterfly needs ~60 more live registers next to the 128 accumulators.)
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // bulk stores have left the stage
+          __syncwarp();
+          const uint32_t rbase = my_stage + (uint32_t)(lane * 128);
+#pragma unroll
+          for (int c = 0; c < CH / 32; ++c) {
+            const int col0 = n0 + chalf * CH + c * 32;
+            if (col0 >= No) continue;                            // warp-uniform
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (uint32_t)(((q ^ (lane & 7)) << 4))), "f"(acc[c * 32 + 4 * q]),
+                           "f"(acc[c * 32 + 4 * q + 1]), "f"(acc[c * 32 + 4 * q + 2]), "f"(acc[c * 32 + 4 * q + 3])
+                           : "memory");
+            __syncwarp();
+            float csum = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              float x;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(my_stage + (uint32_t)(r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)))) : "memory");
+              csum += x;
+            }
+            __syncwarp();
+            if (col0 + lane < No) atomicAdd(ep.colsum + col0 + lane, csum * inv_s_tile);
           }
         }
       }
-      if (ep.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if ((ep.tma_store || ep.emit_h) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       if (ep.amax_out) {
         const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(out_max));   // non-negative floats order like uints
         if (lane == 0 && m) atomicMax(ep.amax_out, m);
@@ -616,12 +769,16 @@ struct Operand {
   const __half* hi; int rows; int cols; int ld_h; bool mn_major;
   const __half* lo() const { return hi + (size_t)rows * ld_h; }
 };
+// companion the epilogue writes (tile-scaled): planes [rows][cols] like an Operand, plus the tile-maxima array
+struct OutH {
+  __half* hi; int rows; int cols; int ld_h; uint32_t* tile_amax; int amax_stride;
+};
 
 template <int BN, bool A_MN, bool B_MN, int CG>
 static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int Mo, int No, int Kc, int splits, EpiParams ep,
-                     cudaStream_t st) {
+                     const OutH* oh, cudaStream_t st) {
   using K = Cfg<BN, CG>;
-  CUtensorMap mah, mal, mbh, mbl, mc;
+  CUtensorMap mah, mal, mbh, mbl, mc, moh, mol;
   if (int rc = make_map(&mah, A.hi, A.rows, A.cols, A.ld_h, A_MN, BM)) return rc;
   if (int rc = make_map(&mal, A.lo(), A.rows, A.cols, A.ld_h, A_MN, BM)) return rc;
   if (int rc = make_map(&mbh, B.hi, B.rows, B.cols, B.ld_h, B_MN, K::B_ROWS)) return rc;
@@ -629,7 +786,28 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
   ep.dbg = g_dbg;
   // plain overwrites leave through shared memory + bulk tensor stores (32 x 32 fp32 boxes, SWIZZLE_128B); accumulating /
   // atomic epilogues and outputs the TMA cannot address (pitch or base not 16-byte aligned) store directly
-  ep.tma_store = (!ep.accumulate && !ep.atomic && !(g_dbg & 2) && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
+  ep.write_f32 = C ? 1 : 0;
+  ep.tma_store = (C && !ep.accumulate && !ep.atomic && !(g_dbg & 2) && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
+  ep.emit_h = 0;
+  moh = mah; mol = mah;   // unused unless the epilogue emits a companion
+  if (oh) {
+    if (BN != 256) { set_error("the epilogue emits companions for 256-wide output tiles only"); return GCBF_E_UNSUPPORTED; }
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return GCBF_E_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)oh->cols, (cuuint64_t)oh->rows};
+    cuuint64_t strides[1] = {(cuuint64_t)oh->ld_h * 2};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    for (int plane = 0; plane < 2; ++plane) {
+      CUresult r = fn(plane ? &mol : &moh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, oh->hi + (size_t)plane * oh->rows * oh->ld_h, dims, strides, box,
+                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output companion) failed (%d) M=%d N=%d ld=%d", (int)r, oh->rows, oh->cols, oh->ld_h); return GCBF_E_CUDA; }
+    }
+    ep.emit_h = 1;
+    ep.out_tile_amax = oh->tile_amax;
+    ep.out_amax_stride = oh->amax_stride;
+  }
   if (ep.tma_store) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return GCBF_E_CUDA; }
@@ -650,7 +828,8 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
   }
   const int tiles_m = ceil_div(Mo, BM * CG), tiles_n = ceil_div(No, BN);   // CG == 2: 256-row pair tiles
   const int kblocks = ceil_div(Kc, BK);
-  const int kps = ceil_div(kblocks, splits);
+  // chunks of g_kch k-blocks must not straddle splits (tile-scaled operands: a chunk lies inside one scale tile)
+  const int kps = ceil_div(ceil_div(kblocks, splits), g_kch) * g_kch;
   const int nsplit = ceil_div(kblocks, kps);
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
@@ -669,7 +848,7 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CG == 2) ? 1 : 0;
-  GCBF_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_h_kernel<BN, A_MN, B_MN, CG>, mah, mal, mbh, mbl, mc, C, ldc, Mo, No, tiles_m, tiles_n, kps,
+  GCBF_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_h_kernel<BN, A_MN, B_MN, CG>, mah, mal, mbh, mbl, mc, moh, mol, C, ldc, Mo, No, tiles_m, tiles_n, kps,
                                   kblocks, g_kch, ep));
   return GCBF_OK;
 }
@@ -677,7 +856,7 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
 // CTA pairs (cta_group::2) for the 256-wide tiles unless GCBF_TC_2CTA=0
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo, int No, int Kc, int splits, EpiParams ep,
-                  cudaStream_t st) {
+                  const OutH* oh, cudaStream_t st) {
   if (g_dbg < 0) {
     const char* d = getenv("GCBF_TC_DBG");
     g_dbg = d ? atoi(d) : 0;
@@ -686,8 +865,9 @@ static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo,
     const char* kc = getenv("GCBF_TC_KCH");
     if (kc && atoi(kc) >= 1 && atoi(kc) <= KCH_MAX) g_kch = atoi(kc);
   }
-  if (BN == 256 && g_two_cta) return launch_cg<256, A_MN, B_MN, 2>(A, B, C, ldc, Mo, No, Kc, splits, ep, st);
-  return launch_cg<BN, A_MN, B_MN, 1>(A, B, C, ldc, Mo, No, Kc, splits, ep, st);
+  if ((ep.a_sr || ep.a_sc || ep.b_sr || ep.b_sc) && g_kch > 4) { set_error("tile-scaled operands need promotion chunks of <= 128 K-elements (GCBF_TC_KCH <= 4)"); return GCBF_E_UNSUPPORTED; }
+  if (BN == 256 && g_two_cta) return launch_cg<256, A_MN, B_MN, 2>(A, B, C, ldc, Mo, No, Kc, splits, ep, oh, st);
+  return launch_cg<BN, A_MN, B_MN, 1>(A, B, C, ldc, Mo, No, Kc, splits, ep, oh, st);
 }
 
 static int check_plane(const void* p, int ld_h, const char* what) {
@@ -774,61 +954,119 @@ extern "C" int gcbf_linear_h_supported(int M, int N, int K) {
   return (M >= 256 && N >= 96 && K >= 96 && (long long)M * N * K >= (1ll << 24)) ? 1 : 0;
 }
 
-// Y[M,N] = act(alpha * X W^T + bias): A = X companion [M][K] (K-major), B = W companion [N][K] (K-major)
-extern "C" int gcbf_linear_fwd_h(const void* Xh, int ldxh, const void* x_amax, const void* Wh, int ldwh, const void* w_amax,
-                                 const float* bias, const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act,
-                                 void* out_amax, void* stream) {
-  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && ldy >= N && Y && x_amax && w_amax, "gcbf_linear_fwd_h: bad arguments M=%d N=%d K=%d", M, N, K);
-  if (int rc = th::check_plane(Xh, ldxh, "gcbf_linear_fwd_h X")) return rc;
-  if (int rc = th::check_plane(Wh, ldwh, "gcbf_linear_fwd_h W")) return rc;
+static int check_h16(const gcbf_h16* h, const char* what, int rows, int cols) {
+  if (!h || !h->buf || !h->amax || h->rows != rows || h->cols != cols || h->ld < cols) {
+    set_error("%s: companion descriptor (expected [%d x %d])", what, rows, cols);
+    return GCBF_E_INVALID;
+  }
+  return th::check_plane(h->buf, h->ld, what);
+}
+
+// Y[M,N] = act(alpha * X W^T + bias): A = X companion [M][K] (K-major), B = W companion [N][K] (K-major, per-tensor scale)
+extern "C" int gcbf_linear_fwd_t(const gcbf_h16* X, const gcbf_h16* W, const float* bias, const float* inv_sigma, int act, float* Y, int ldy,
+                                 const gcbf_h16* Yh, void* out_amax, int M, int N, int K, void* stream) {
+  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && (Y || Yh) && (!Y || ldy >= N), "gcbf_linear_fwd_t: bad arguments M=%d N=%d K=%d", M, N, K);
+  if (int rc = check_h16(X, "gcbf_linear_fwd_t X", M, K)) return rc;
+  if (int rc = check_h16(W, "gcbf_linear_fwd_t W", N, K)) return rc;
+  GCBF_REQUIRE(W->amax_row_stride == 0 && W->amax_col_stride == 0, "gcbf_linear_fwd_t: the weight companion must be per-tensor scaled");
   cudaStream_t st = as_stream(stream);
   th::EpiParams ep{};
   ep.mode = th::EPI_FWD; ep.alpha = inv_sigma; ep.bias = bias; ep.act = act;
-  ep.amax_a = reinterpret_cast<const uint32_t*>(x_amax); ep.amax_b = reinterpret_cast<const uint32_t*>(w_amax);
+  ep.amax_a = reinterpret_cast<const uint32_t*>(X->amax); ep.a_sr = X->amax_row_stride; ep.a_sc = X->amax_col_stride;
+  ep.amax_b = reinterpret_cast<const uint32_t*>(W->amax);
   ep.amax_out = reinterpret_cast<uint32_t*>(out_amax);
   if (out_amax) GCBF_CUDA_OK(cudaMemsetAsync(out_amax, 0, 4, st));
-  th::Operand A{reinterpret_cast<const __half*>(Xh), M, K, ldxh, false}, B{reinterpret_cast<const __half*>(Wh), N, K, ldwh, false};
-  return (N > 128) ? th::launch<256, false, false>(A, B, Y, ldy, M, N, K, 1, ep, st)
-                   : th::launch<128, false, false>(A, B, Y, ldy, M, N, K, 1, ep, st);
+  th::OutH oh{};
+  if (Yh) {
+    if (int rc = check_h16(Yh, "gcbf_linear_fwd_t Yh", M, N)) return rc;
+    GCBF_REQUIRE(N > 128 && Yh->amax_row_stride == ceil_div(N, 256) && Yh->amax_col_stride == 1, "gcbf_linear_fwd_t: emitted companions are tile-scaled (N > 128, amax strides (ceil(N/256), 1))");
+    oh = th::OutH{reinterpret_cast<__half*>(Yh->buf), M, N, Yh->ld, reinterpret_cast<uint32_t*>(Yh->amax), Yh->amax_row_stride};
+  }
+  th::Operand A{reinterpret_cast<const __half*>(X->buf), M, K, X->ld, false}, B{reinterpret_cast<const __half*>(W->buf), N, K, W->ld, false};
+  return (N > 128) ? th::launch<256, false, false>(A, B, Y, ldy, M, N, K, 1, ep, Yh ? &oh : nullptr, st)
+                   : th::launch<128, false, false>(A, B, Y, ldy, M, N, K, 1, ep, nullptr, st);
 }
 
 // dX[M,K] (+)= alpha * dZ W (* relu mask): A = dZ companion [M][N] (K-major: contraction over N), B = W companion [N][K] (MN-major)
-extern "C" int gcbf_linear_bwd_data_h(const void* dZh, int lddzh, const void* dz_amax, const void* Wh, int ldwh,
-                                      const void* w_amax, const float* inv_sigma, const float* relu_src, int ld_relu, float* dX,
-                                      int lddx, int M, int N, int K, int accumulate, void* out_amax, void* stream) {
-  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && lddx >= K && dX && dz_amax && w_amax, "gcbf_linear_bwd_data_h: bad arguments M=%d N=%d K=%d", M, N, K);
-  GCBF_REQUIRE(!relu_src || ld_relu >= K, "gcbf_linear_bwd_data_h: ld_relu");
-  if (int rc = th::check_plane(dZh, lddzh, "gcbf_linear_bwd_data_h dZ")) return rc;
-  if (int rc = th::check_plane(Wh, ldwh, "gcbf_linear_bwd_data_h W")) return rc;
+extern "C" int gcbf_linear_bwd_data_t(const gcbf_h16* dZ, const gcbf_h16* W, const float* inv_sigma, const float* relu_src, int ld_relu,
+                                      const gcbf_h16* relu_h, float* dX, int lddx, int accumulate, const gcbf_h16* dXh, float* colsum,
+                                      void* out_amax, int M, int N, int K, void* stream) {
+  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && (dX || dXh) && (!dX || lddx >= K), "gcbf_linear_bwd_data_t: bad arguments M=%d N=%d K=%d", M, N, K);
+  GCBF_REQUIRE(!relu_src || ld_relu >= K, "gcbf_linear_bwd_data_t: ld_relu");
+  GCBF_REQUIRE(!(relu_src && relu_h) && !(accumulate && (dXh || colsum)), "gcbf_linear_bwd_data_t: conflicting options");
+  if (int rc = check_h16(dZ, "gcbf_linear_bwd_data_t dZ", M, N)) return rc;
+  if (int rc = check_h16(W, "gcbf_linear_bwd_data_t W", N, K)) return rc;
+  GCBF_REQUIRE(W->amax_row_stride == 0 && W->amax_col_stride == 0, "gcbf_linear_bwd_data_t: the weight companion must be per-tensor scaled");
+  if (relu_h) { if (int rc = check_h16(relu_h, "gcbf_linear_bwd_data_t relu_h", M, K)) return rc; }
   cudaStream_t st = as_stream(stream);
   th::EpiParams ep{};
   ep.mode = th::EPI_DGRAD; ep.alpha = inv_sigma; ep.relu_src = relu_src; ep.ld_relu = ld_relu; ep.accumulate = accumulate;
-  ep.amax_a = reinterpret_cast<const uint32_t*>(dz_amax); ep.amax_b = reinterpret_cast<const uint32_t*>(w_amax);
+  if (relu_h) { ep.relu_hi = reinterpret_cast<const __half*>(relu_h->buf); ep.ld_relu_h = relu_h->ld; }
+  ep.amax_a = reinterpret_cast<const uint32_t*>(dZ->amax); ep.a_sr = dZ->amax_row_stride; ep.a_sc = dZ->amax_col_stride;
+  ep.amax_b = reinterpret_cast<const uint32_t*>(W->amax);
   ep.amax_out = reinterpret_cast<uint32_t*>(out_amax);
+  ep.colsum = colsum;
   if (out_amax) GCBF_CUDA_OK(cudaMemsetAsync(out_amax, 0, 4, st));
-  th::Operand A{reinterpret_cast<const __half*>(dZh), M, N, lddzh, false}, B{reinterpret_cast<const __half*>(Wh), N, K, ldwh, true};
-  return (K > 128) ? th::launch<256, false, true>(A, B, dX, lddx, M, K, N, 1, ep, st)
-                   : th::launch<128, false, true>(A, B, dX, lddx, M, K, N, 1, ep, st);
+  th::OutH oh{};
+  if (dXh) {
+    if (int rc = check_h16(dXh, "gcbf_linear_bwd_data_t dXh", M, K)) return rc;
+    GCBF_REQUIRE(K > 128 && dXh->amax_row_stride == ceil_div(K, 256) && dXh->amax_col_stride == 1, "gcbf_linear_bwd_data_t: emitted companions are tile-scaled (K > 128, amax strides (ceil(K/256), 1))");
+    oh = th::OutH{reinterpret_cast<__half*>(dXh->buf), M, K, dXh->ld, reinterpret_cast<uint32_t*>(dXh->amax), dXh->amax_row_stride};
+  }
+  th::Operand A{reinterpret_cast<const __half*>(dZ->buf), M, N, dZ->ld, false}, B{reinterpret_cast<const __half*>(W->buf), N, K, W->ld, true};
+  return (K > 128) ? th::launch<256, false, true>(A, B, dX, lddx, M, K, N, 1, ep, dXh ? &oh : nullptr, st)
+                   : th::launch<128, false, true>(A, B, dX, lddx, M, K, N, 1, ep, nullptr, st);
 }
 
 // dW[N,K] (+)= alpha * dZ^T X: A = dZ companion [M][N] (MN-major), B = X companion [M][K] (MN-major); contraction over M
-extern "C" int gcbf_linear_bwd_weight_h(const void* dZh, int lddzh, const void* dz_amax, const void* Xh, int ldxh,
-                                        const void* x_amax, const float* inv_sigma, float* dW, int lddw, int M, int N, int K,
-                                        int accumulate, void* stream) {
-  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && lddw >= K && dW && dz_amax && x_amax, "gcbf_linear_bwd_weight_h: bad arguments M=%d N=%d K=%d", M, N, K);
-  if (int rc = th::check_plane(dZh, lddzh, "gcbf_linear_bwd_weight_h dZ")) return rc;
-  if (int rc = th::check_plane(Xh, ldxh, "gcbf_linear_bwd_weight_h X")) return rc;
+extern "C" int gcbf_linear_bwd_weight_t(const gcbf_h16* dZ, const gcbf_h16* X, const float* inv_sigma, float* dW, int lddw, int accumulate,
+                                        int M, int N, int K, void* stream) {
+  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && lddw >= K && dW, "gcbf_linear_bwd_weight_t: bad arguments M=%d N=%d K=%d", M, N, K);
+  if (int rc = check_h16(dZ, "gcbf_linear_bwd_weight_t dZ", M, N)) return rc;
+  if (int rc = check_h16(X, "gcbf_linear_bwd_weight_t X", M, K)) return rc;
   cudaStream_t st = as_stream(stream);
   th::EpiParams ep{};
   ep.mode = th::EPI_WGRAD; ep.alpha = inv_sigma; ep.accumulate = accumulate;
-  ep.amax_a = reinterpret_cast<const uint32_t*>(dz_amax); ep.amax_b = reinterpret_cast<const uint32_t*>(x_amax);
+  ep.amax_a = reinterpret_cast<const uint32_t*>(dZ->amax); ep.a_sr = dZ->amax_row_stride; ep.a_sc = dZ->amax_col_stride;
+  ep.amax_b = reinterpret_cast<const uint32_t*>(X->amax); ep.b_sr = X->amax_row_stride; ep.b_sc = X->amax_col_stride;
   const int BN = (K > 128) ? 256 : 128;
   const int tiles = ceil_div(N, th::BM) * ceil_div(K, BN);
   int splits = 1;
   if (tiles < kNumSMs) splits = max(1, min(ceil_div(M, 256), kNumSMs / tiles));
   ep.atomic = splits > 1;
   if (ep.atomic && !accumulate) GCBF_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)K * 4, N, st));
-  th::Operand A{reinterpret_cast<const __half*>(dZh), M, N, lddzh, true}, B{reinterpret_cast<const __half*>(Xh), M, K, ldxh, true};
-  return (BN == 256) ? th::launch<256, true, true>(A, B, dW, lddw, N, K, M, splits, ep, st)
-                     : th::launch<128, true, true>(A, B, dW, lddw, N, K, M, splits, ep, st);
+  th::Operand A{reinterpret_cast<const __half*>(dZ->buf), M, N, dZ->ld, true}, B{reinterpret_cast<const __half*>(X->buf), M, K, X->ld, true};
+  return (BN == 256) ? th::launch<256, true, true>(A, B, dW, lddw, N, K, M, splits, ep, nullptr, st)
+                     : th::launch<128, true, true>(A, B, dW, lddw, N, K, M, splits, ep, nullptr, st);
+}
+
+// ---- the per-tensor-scaled entry points of ABI v2: thin wrappers ------------------------------------------------------------------------
+static gcbf_h16 per_tensor(const void* buf, int ld, const void* amax, int rows, int cols) {
+  gcbf_h16 h;
+  h.buf = const_cast<void*>(buf); h.amax = const_cast<void*>(amax); h.ld = ld; h.rows = rows; h.cols = cols; h.amax_row_stride = 0; h.amax_col_stride = 0;
+  return h;
+}
+
+extern "C" int gcbf_linear_fwd_h(const void* Xh, int ldxh, const void* x_amax, const void* Wh, int ldwh, const void* w_amax,
+                                 const float* bias, const float* inv_sigma, float* Y, int ldy, int M, int N, int K, int act,
+                                 void* out_amax, void* stream) {
+  GCBF_REQUIRE(Y && x_amax && w_amax, "gcbf_linear_fwd_h: null pointer");
+  const gcbf_h16 X = per_tensor(Xh, ldxh, x_amax, M, K), W = per_tensor(Wh, ldwh, w_amax, N, K);
+  return gcbf_linear_fwd_t(&X, &W, bias, inv_sigma, act, Y, ldy, nullptr, out_amax, M, N, K, stream);
+}
+
+extern "C" int gcbf_linear_bwd_data_h(const void* dZh, int lddzh, const void* dz_amax, const void* Wh, int ldwh,
+                                      const void* w_amax, const float* inv_sigma, const float* relu_src, int ld_relu, float* dX,
+                                      int lddx, int M, int N, int K, int accumulate, void* out_amax, void* stream) {
+  GCBF_REQUIRE(dX && dz_amax && w_amax, "gcbf_linear_bwd_data_h: null pointer");
+  const gcbf_h16 dZ = per_tensor(dZh, lddzh, dz_amax, M, N), W = per_tensor(Wh, ldwh, w_amax, N, K);
+  return gcbf_linear_bwd_data_t(&dZ, &W, inv_sigma, relu_src, ld_relu, nullptr, dX, lddx, accumulate, nullptr, nullptr, out_amax, M, N, K, stream);
+}
+
+extern "C" int gcbf_linear_bwd_weight_h(const void* dZh, int lddzh, const void* dz_amax, const void* Xh, int ldxh,
+                                        const void* x_amax, const float* inv_sigma, float* dW, int lddw, int M, int N, int K,
+                                        int accumulate, void* stream) {
+  GCBF_REQUIRE(dW && dz_amax && x_amax, "gcbf_linear_bwd_weight_h: null pointer");
+  const gcbf_h16 dZ = per_tensor(dZh, lddzh, dz_amax, M, N), X = per_tensor(Xh, ldxh, x_amax, M, K);
+  return gcbf_linear_bwd_weight_t(&dZ, &X, inv_sigma, dW, lddw, accumulate, M, N, K, stream);
 }

@@ -49,7 +49,7 @@ struct Timed {
 int split_h(Run& R, const float* x, int ld, int rows, int cols, const void* amax, float* colsum, H16* out) {
   const int ld_h = (cols + 7) / 8 * 8;
   out->buf = R.ws.alloc((size_t)2 * rows * ld_h * 2);
-  out->ld = ld_h; out->rows = rows; out->cols = cols;
+  out->ld = ld_h; out->rows = rows; out->cols = cols; out->sr = 0; out->sc = 0;
   void* own = nullptr;
   if (!amax) own = R.amax_slot();
   out->amax = amax ? amax : own;
@@ -118,46 +118,99 @@ int sn_power_iter(Run& R, const gcbf_linear_desc* const* layers, int n, bool sna
 }
 
 // ---- MLP chain -------------------------------------------------------------------------------------------------------
-// y = MLP(x).  x_amax: amax word of x when its producer reduced it.  next_width > 0: the output feeds a linear layer of that many
-// out-features; if that one runs on the tensor cores the last layer's epilogue reduces max|y| (-> *y_amax, else nullptr).
-// `out`: where the LAST layer writes (pitch ld_out), or nullptr for a workspace buffer.
-int mlp_forward(Run& R, const gcbf_linear_desc* layers, int n, const float* x, int ldx, int M, const void* x_amax, int next_width,
-                const float* const* inv_sigma, const float* const* us, const float* const* vs, MlpCtx* ctx, float* out, int ld_out,
-                const float** y, int* ldy, const void** y_amax) {
+// Companions written by the producing GEMM's epilogue ("emission", gemm_tcgen05_f16.cu): when a tensor-core layer's output (forward)
+// or input gradient (backward) feeds another tensor-core layer, the producer writes it directly as a tile-scaled fp16 [hi|lo]
+// companion -- no amax pass, no split pass, no fp32 copy in HBM; the ReLU mask of the backward is read from the hi plane and the
+// bias gradient (column sums of dZ) is accumulated by the producing data-grad epilogue.  GCBF_EPI_H=0 keeps the split kernels.
+static int g_epi_h = -1;
+static bool epi_h_enabled() {
+  if (g_epi_h < 0) {
+    const char* e = getenv("GCBF_EPI_H");
+    const char* k = getenv("GCBF_TC_KCH");
+    g_epi_h = (e && e[0] == '0') ? 0 : 1;
+    if (k && atoi(k) > 4) g_epi_h = 0;          // tile-scaled operands need promotion chunks of <= 128 K-elements
+  }
+  return g_epi_h == 1 && g_gemm_impl != 1;
+}
+// may a [M, width] tensor produced by a tensor-core layer be emitted as a companion for a consumer layer with `consumer_n` outputs?
+static bool can_emit(int M, int width, int consumer_n) { return epi_h_enabled() && width > 128 && consumer_n > 0 && use_h(M, consumer_n, width); }
+
+static gcbf_h16 h16_desc(const H16& h) {
+  gcbf_h16 d;
+  d.buf = h.buf; d.amax = const_cast<void*>(h.amax); d.ld = h.ld; d.rows = h.rows; d.cols = h.cols;
+  d.amax_row_stride = h.sr; d.amax_col_stride = h.sc; d.pad_ = 0;
+  return d;
+}
+static gcbf_h16 weight_desc(const gcbf_linear_desc& L) {
+  gcbf_h16 d;
+  d.buf = L.Wh; d.amax = L.w_amax; d.ld = L.ldwh; d.rows = L.N; d.cols = L.K; d.amax_row_stride = 0; d.amax_col_stride = 0; d.pad_ = 0;
+  return d;
+}
+// buffers of a tile-scaled companion an epilogue is about to write
+static H16 alloc_tiled(Run& R, int rows, int cols) {
+  H16 h{};
+  h.ld = (cols + 7) / 8 * 8; h.rows = rows; h.cols = cols;
+  h.buf = R.ws.alloc((size_t)2 * rows * h.ld * 2);
+  h.sr = (cols + 255) / 256; h.sc = 1;
+  h.amax = R.ws.alloc((size_t)((rows + 127) / 128) * h.sr * 4);
+  return h;
+}
+
+// y = MLP(x).  x: fp32 input (may be nullptr when x_h is given); x_h: its companion if a producer emitted one; x_amax: per-tensor
+// amax word of x when its producer reduced it.  next_width > 0: the output feeds a linear layer of that many out-features.
+// `out`: where the LAST layer writes its fp32 output (pitch ld_out), or nullptr for a workspace buffer; out_h (optional): receives the
+// emitted companion of the output when the consumer qualifies (buf == nullptr otherwise) -- the fp32 output is then written only
+// if need_f32_out.
+int mlp_forward(Run& R, const gcbf_linear_desc* layers, int n, const float* x, int ldx, int M, const H16* x_h, const void* x_amax,
+                int next_width, const float* const* inv_sigma, const float* const* us, const float* const* vs, MlpCtx* ctx, float* out,
+                int ld_out, bool need_f32_out, H16* out_h, const float** y, int* ldy, const void** y_amax) {
   if (ctx) { memset(ctx, 0, sizeof(*ctx)); ctx->n = n; ctx->M = M; ctx->acts[0] = x; ctx->ld[0] = ldx; }
   const float* cur = x;
   int ldc = ldx;
+  H16 cur_h = x_h ? *x_h : H16{};
   const void* cur_amax = x_amax;
+  if (out_h) *out_h = H16{};
   for (int l = 0; l < n; ++l) {
     const gcbf_linear_desc& L = layers[l];
     const int N = L.N, K = L.K;
-    const int nxt = (l + 1 < n) ? layers[l + 1].N : next_width;
-    void* ya = (nxt > 0 && use_h(M, nxt, N)) ? R.amax_slot() : nullptr;
-    float* dst; int ldd;
-    if (l == n - 1 && out) { dst = out; ldd = ld_out; }
-    else { dst = (float*)R.ws.alloc((size_t)M * N * 4); ldd = N; }
-    H16 xh{};
-    bool h = use_h(M, N, K) && M > 0;
+    const bool lastl = (l == n - 1);
+    const int nxt = !lastl ? layers[l + 1].N : next_width;
+    const bool h = use_h(M, N, K) && M > 0;
+    const bool emit = h && can_emit(M, N, nxt) && (!lastl || out_h != nullptr);
+    const bool f32 = !emit || (lastl && need_f32_out);
+    void* ya = (!emit && nxt > 0 && use_h(M, nxt, N)) ? R.amax_slot() : nullptr;
+    float* dst = nullptr; int ldd = N;
+    if (f32) {
+      if (lastl && out) { dst = out; ldd = ld_out; }
+      else dst = (float*)R.ws.alloc((size_t)M * N * 4);
+    }
+    H16 yh{};
     if (h) {
       if (!L.Wh) { set_error("layer [%d x %d] runs on the tensor cores but its descriptor has no weight companion", N, K); return GCBF_E_INVALID; }
-      if (int rc = split_h(R, cur, ldc, M, K, cur_amax, nullptr, &xh)) return rc;
+      if (!cur_h.buf) { if (int rc = split_h(R, cur, ldc, M, K, cur_amax, nullptr, &cur_h)) return rc; }
+      if (emit) yh = alloc_tiled(R, M, N);
       if (!R.dry) {
         Timed t(R, 0, 2.0 * M * N * K, M, N, K);
-        CHAIN_CALL(gcbf_linear_fwd_h(xh.buf, xh.ld, xh.amax, L.Wh, L.ldwh, L.w_amax, L.b, inv_sigma[l], dst, ldd, M, N, K, L.act, ya, R.st));
+        const gcbf_h16 X = h16_desc(cur_h), W = weight_desc(L), Y = h16_desc(yh);
+        CHAIN_CALL(gcbf_linear_fwd_t(&X, &W, L.b, inv_sigma[l], L.act, dst, ldd, emit ? &Y : nullptr, ya, M, N, K, R.st));
         R.launched(1);
       }
-    } else if (!R.dry) {
-      Timed t(R, 3, 2.0 * M * N * K, M, N, K);
-      CHAIN_CALL(gcbf_linear_fwd(cur, ldc, L.W, L.ldw, L.b, inv_sigma[l], dst, ldd, M, N, K, L.act, g_gemm_impl == 1 ? 1 : 0, ya, R.st));
-      R.launched(ya ? 2 : 1);
+    } else {
+      if (!cur && M > 0) { set_error("mlp_forward: layer %d needs its fp32 input", l); return GCBF_E_INVALID; }
+      if (!R.dry) {
+        Timed t(R, 3, 2.0 * M * N * K, M, N, K);
+        CHAIN_CALL(gcbf_linear_fwd(cur, ldc, L.W, L.ldw, L.b, inv_sigma[l], dst, ldd, M, N, K, L.act, g_gemm_impl == 1 ? 1 : 0, ya, R.st));
+        R.launched(ya ? 2 : 1);
+      }
     }
     if (ctx) {
       ctx->acts[l + 1] = dst; ctx->ld[l + 1] = ldd;
-      ctx->acts_h[l] = h ? xh : H16{};
+      ctx->acts_h[l] = h ? cur_h : H16{};
       ctx->inv_sigma[l] = inv_sigma[l]; ctx->u[l] = us[l]; ctx->v[l] = vs[l];
     }
-    cur = dst; ldc = ldd; cur_amax = ya;
+    cur = dst; ldc = ldd; cur_amax = ya; cur_h = yh;
   }
+  if (out_h) *out_h = cur_h;
   *y = cur; *ldy = ldc;
   if (y_amax) *y_amax = cur_amax;
   return 0;
@@ -175,19 +228,25 @@ int vec_add(Run& R, float* dst, const float* src, int64_t n) {
   return 0;
 }
 
-// Backward of the chain.  dy [M, N_last] (pitch ld_dy); dy_amax: its amax word if the producer reduced it (only meaningful when
-// the last layer has no activation).  need_dx: produce the input gradient -- into dx_out (pitch ld_dx, optionally accumulated) or
-// a workspace buffer; dx_amax: word that receives max|dx| if the input-gradient GEMM runs on the tensor cores (*dx_amax_valid).
-int mlp_backward(Run& R, const gcbf_linear_desc* layers, int n, const MlpCtx& ctx, const float* dy, int ld_dy, bool need_dx,
-                 float* dx_out, int ld_dx, bool dx_accumulate, const void* dy_amax, void* dx_amax, bool skip_wgrad, const float** dx,
-                 int* ld_dx_res, bool* dx_amax_valid) {
+// Backward of the chain.  dy [M, N_last] (pitch ld_dy) -- or its emitted companion dy_h (then dy may be nullptr and the bias gradient
+// of the last layer has already been accumulated by the producer iff dy_colsum_done); dy_amax: per-tensor amax word of dy if the
+// producer reduced it.  need_dx: produce the input gradient -- into dx_out (pitch ld_dx, optionally accumulated) or a workspace
+// buffer; dx_amax: word that receives max|dx| if the input-gradient GEMM runs on the tensor cores (*dx_amax_valid).  dx_h (optional):
+// the caller's consumer is a tensor-core layer with `dx_consumer_n` outputs whose bias gradient lives at dx_colsum: if the producer
+// qualifies, dx is emitted as a companion only (*dx == nullptr, dx_h->buf != nullptr) and its column sums are added to dx_colsum.
+int mlp_backward(Run& R, const gcbf_linear_desc* layers, int n, const MlpCtx& ctx, const float* dy, int ld_dy, const H16* dy_h,
+                 bool dy_colsum_done, bool need_dx, float* dx_out, int ld_dx, bool dx_accumulate, const void* dy_amax, void* dx_amax,
+                 bool skip_wgrad, H16* dx_h, int dx_consumer_n, float* dx_colsum, const float** dx, int* ld_dx_res, bool* dx_amax_valid) {
   const int M = ctx.M;
   const int last = n - 1;
   const float* dz = dy;
   int lddz = ld_dy;
+  H16 dzh = dy_h ? *dy_h : H16{};
+  bool colsum_done = dy_h ? dy_colsum_done : false;
+  if (dx_h) *dx_h = H16{};
   if (layers[last].act != GCBF_ACT_NONE) {
     const int N = layers[last].N;
-    if (ld_dy != N || ctx.ld[last + 1] != N) { set_error("mlp_backward: output activation needs dense d_out / output"); return GCBF_E_INVALID; }
+    if (!dz || ld_dy != N || ctx.ld[last + 1] != N || !ctx.acts[last + 1]) { set_error("mlp_backward: output activation needs dense fp32 d_out / output"); return GCBF_E_INVALID; }
     float* t = (float*)R.ws.alloc((size_t)M * N * 4);
     if (!R.dry) { CHAIN_CALL(gcbf_act_bwd(dz, ctx.acts[last + 1], t, (int64_t)M * N, layers[last].act, R.st)); R.launched(1); }
     dz = t;
@@ -203,54 +262,76 @@ int mlp_backward(Run& R, const gcbf_linear_desc* layers, int n, const MlpCtx& ct
     const bool wgrad = !skip_wgrad && L.gW;
     if (use_h(M, N, K) && M > 0) {
       // one fp16 companion of dz serves the weight-grad (MN-major A) and the data-grad (K-major A); the bias gradient (column
-      // sums of dz) is fused into the split
-      H16 dzh{};
-      if (int rc = split_h(R, dz, lddz, M, N, dz_amax, (wgrad && L.gb) ? L.gb : nullptr, &dzh)) return rc;
+      // sums of dz) is fused into the split -- or was accumulated by the epilogue that emitted the companion
+      if (!dzh.buf) {
+        if (int rc = split_h(R, dz, lddz, M, N, dz_amax, (wgrad && L.gb) ? L.gb : nullptr, &dzh)) return rc;
+      } else if (wgrad && L.gb && !colsum_done) {
+        set_error("mlp_backward: emitted gradient companion without its bias gradient"); return GCBF_E_INVALID;
+      }
+      const gcbf_h16 dZ = h16_desc(dzh), W = weight_desc(L);
       if (wgrad) {
         H16 xh = ctx.acts_h[l];
         if (!xh.buf) { if (int rc = split_h(R, x_in, ldx, M, K, nullptr, nullptr, &xh)) return rc; }
+        const gcbf_h16 X = h16_desc(xh);
         if (L.u) {
           float* dW = (float*)R.ws.alloc((size_t)N * K * 4);
           float* fx = (float*)R.ws.alloc(gcbf_sn_workspace_floats(N, K) * 4);
           if (!R.dry) {
             { Timed t(R, 2, 2.0 * M * N * K, M, N, K);
-              CHAIN_CALL(gcbf_linear_bwd_weight_h(dzh.buf, dzh.ld, dzh.amax, xh.buf, xh.ld, xh.amax, isg, dW, K, M, N, K, 0, R.st)); }
+              CHAIN_CALL(gcbf_linear_bwd_weight_t(&dZ, &X, isg, dW, K, 0, M, N, K, R.st)); }
             CHAIN_CALL(gcbf_sn_grad_fixup(dW, K, L.W, L.ldw, N, K, ctx.u[l], ctx.v[l], isg, fx, L.gW, L.ldgw, R.st));
             R.launched(3);
           }
         } else if (!R.dry) {
           Timed t(R, 2, 2.0 * M * N * K, M, N, K);
-          CHAIN_CALL(gcbf_linear_bwd_weight_h(dzh.buf, dzh.ld, dzh.amax, xh.buf, xh.ld, xh.amax, isg, L.gW, L.ldgw, M, N, K, 1, R.st));
+          CHAIN_CALL(gcbf_linear_bwd_weight_t(&dZ, &X, isg, L.gW, L.ldgw, 1, M, N, K, R.st));
           R.launched(1);
         }
       }
+      // ReLU mask of the layer below: from its fp32 output, or from the hi plane of that output's companion
+      const gcbf_h16 maskh = h16_desc(ctx.acts_h[l]);
+      const bool mask_h = (x_in == nullptr);
       if (l > 0) {
-        const int Kp = layers[l - 1].K;
-        void* na = use_h(M, K, Kp) ? R.amax_slot() : nullptr;
-        float* o = (float*)R.ws.alloc((size_t)M * K * 4);
+        const gcbf_linear_desc& P = layers[l - 1];
+        const bool emit = can_emit(M, K, P.K) && use_h(M, P.N, P.K);
+        const bool pw = !skip_wgrad && P.gW && P.gb;
+        void* na = (!emit && use_h(M, K, P.K)) ? R.amax_slot() : nullptr;
+        float* o = emit ? nullptr : (float*)R.ws.alloc((size_t)M * K * 4);
+        H16 oh{};
+        if (emit) oh = alloc_tiled(R, M, K);
         if (!R.dry) {
           Timed t(R, 1, 2.0 * M * N * K, M, N, K);
-          CHAIN_CALL(gcbf_linear_bwd_data_h(dzh.buf, dzh.ld, dzh.amax, L.Wh, L.ldwh, L.w_amax, isg, x_in, ldx, o, K, M, N, K, 0, na, R.st));
+          const gcbf_h16 O = h16_desc(oh);
+          CHAIN_CALL(gcbf_linear_bwd_data_t(&dZ, &W, isg, mask_h ? nullptr : x_in, ldx, mask_h ? &maskh : nullptr, o, K, 0, emit ? &O : nullptr,
+                                            (emit && pw) ? P.gb : nullptr, na, M, N, K, R.st));
           R.launched(1);
         }
-        dz = o; lddz = K; dz_amax = na;
+        dz = o; lddz = K; dz_amax = na; dzh = oh; colsum_done = emit && pw;
       } else if (need_dx) {
+        const bool emit = dx_h && !dx_out && !dx_accumulate && can_emit(M, K, dx_consumer_n);
         float* o = dx_out; int ldo = ld_dx;
-        if (!o) { o = (float*)R.ws.alloc((size_t)M * K * 4); ldo = K; }
+        if (!o && !emit) { o = (float*)R.ws.alloc((size_t)M * K * 4); ldo = K; }
+        H16 oh{};
+        if (emit) oh = alloc_tiled(R, M, K);
         if (!R.dry) {
           Timed t(R, 1, 2.0 * M * N * K, M, N, K);
-          CHAIN_CALL(gcbf_linear_bwd_data_h(dzh.buf, dzh.ld, dzh.amax, L.Wh, L.ldwh, L.w_amax, isg, nullptr, 0, o, ldo, M, N, K,
-                                            dx_accumulate ? 1 : 0, dx_amax, R.st));
+          const gcbf_h16 O = h16_desc(oh);
+          CHAIN_CALL(gcbf_linear_bwd_data_t(&dZ, &W, isg, nullptr, 0, nullptr, o, ldo, dx_accumulate ? 1 : 0, emit ? &O : nullptr,
+                                            (emit && !skip_wgrad) ? dx_colsum : nullptr, emit ? nullptr : dx_amax, M, N, K, R.st));
           R.launched(1);
         }
         dz = o; lddz = ldo;
-        if (dx_amax_valid) *dx_amax_valid = dx_amax != nullptr;
+        if (emit) *dx_h = oh;
+        if (dx_amax_valid) *dx_amax_valid = (!emit && dx_amax != nullptr);
       } else {
         dz = nullptr;
       }
-      continue;
+      if (l > 0) continue;
+      break;
     }
+    if (!dz && M > 0) { set_error("mlp_backward: layer %d needs its fp32 output gradient", l); return GCBF_E_INVALID; }
     dz_amax = nullptr;
+    dzh = H16{};
     const int impl = g_gemm_impl == 1 ? 1 : 0;
     if (wgrad) {
       if (L.u) {
@@ -353,10 +434,13 @@ int net_forward(Run& R, const gcbf_net_desc& net, const float* x, const float* e
   const float *msg, *gate, *feat;
   int ldm, ldg, ldf;
   const void *msg_amax = nullptr, *feat_amax = nullptr;
-  if (int rc = mlp_forward(R, net.phi, net.n_phi, ein, kin, E, nullptr, net.gate[0].N, isg, us, vs, save ? &ctx->phi : nullptr, nullptr, 0,
-                           &msg, &ldm, &msg_amax)) return rc;                                   // gnn.py:30-32
-  if (int rc = mlp_forward(R, net.gate, net.n_gate, msg, ldm, E, msg_amax, 0, isg + o_gate, us + o_gate, vs + o_gate,
-                           save ? &ctx->gate : nullptr, nullptr, 0, &gate, &ldg, nullptr)) return rc;   // AttentionalAggregation.gate_nn
+  H16 msg_h{}, feat_h{};
+  // phi's output is needed twice: as fp32 by the aggregation and (as a companion, when the gate's first layer is a tensor-core
+  // layer) by gate_nn -- the last phi layer writes both
+  if (int rc = mlp_forward(R, net.phi, net.n_phi, ein, kin, E, nullptr, nullptr, net.gate[0].N, isg, us, vs, save ? &ctx->phi : nullptr, nullptr, 0,
+                           true, &msg_h, &msg, &ldm, &msg_amax)) return rc;                      // gnn.py:30-32
+  if (int rc = mlp_forward(R, net.gate, net.n_gate, msg, ldm, E, msg_h.buf ? &msg_h : nullptr, msg_amax, 0, isg + o_gate, us + o_gate, vs + o_gate,
+                           save ? &ctx->gate : nullptr, nullptr, 0, true, nullptr, &gate, &ldg, nullptr)) return rc;   // AttentionalAggregation.gate_nn
   float* gin_all = (float*)R.ws.alloc((size_t)Nn * (C + nd) * 4);
   float* att = (float*)R.ws.alloc((size_t)E * 4);
   if (!R.dry) {
@@ -372,9 +456,10 @@ int net_forward(Run& R, const gcbf_net_desc& net, const float* x, const float* e
   }
   const bool has_head = net.n_head > 0;
   const bool chain_head = has_head && net.head_extra_dim == 0;                          // the head reads gamma's output in place
-  if (int rc = mlp_forward(R, net.gamma, net.n_gamma, gin, C + nd, rows, nullptr, chain_head ? net.head[0].N : 0, isg + o_gamma,
-                           us + o_gamma, vs + o_gamma, save ? &ctx->gamma : nullptr, has_head ? nullptr : out, ld_out, &feat, &ldf,
-                           &feat_amax)) return rc;                                                // gnn.py:34-36
+  // gamma's output feeds the head directly when nothing is concatenated (CBF): then only its companion is written
+  if (int rc = mlp_forward(R, net.gamma, net.n_gamma, gin, C + nd, rows, nullptr, nullptr, chain_head ? net.head[0].N : 0, isg + o_gamma,
+                           us + o_gamma, vs + o_gamma, save ? &ctx->gamma : nullptr, has_head ? nullptr : out, ld_out, !chain_head,
+                           chain_head ? &feat_h : nullptr, &feat, &ldf, &feat_amax)) return rc;   // gnn.py:34-36
   if (has_head) {
     const int F = net.gamma[net.n_gamma - 1].N;
     const float* hin = feat;
@@ -389,8 +474,9 @@ int net_forward(Run& R, const gcbf_net_desc& net, const float* x, const float* e
       hin = hcat; ldh = F + net.head_extra_dim;
     }
     const float* y; int ldy;
-    if (int rc = mlp_forward(R, net.head, net.n_head, hin, ldh, rows, chain_head ? feat_amax : nullptr, 0, isg + o_head, us + o_head,
-                             vs + o_head, save ? &ctx->head : nullptr, out, ld_out, &y, &ldy, nullptr)) return rc;
+    if (int rc = mlp_forward(R, net.head, net.n_head, hin, ldh, rows, (chain_head && feat_h.buf) ? &feat_h : nullptr,
+                             chain_head ? feat_amax : nullptr, 0, isg + o_head, us + o_head, vs + o_head, save ? &ctx->head : nullptr, out,
+                             ld_out, true, nullptr, &y, &ldy, nullptr)) return rc;
   }
   if (ctx) { ctx->msg = msg; ctx->att = att; }
   return 0;
@@ -403,17 +489,23 @@ int net_backward(Run& R, const gcbf_net_desc& net, const NetCtx& ctx, const int3
   const float* d_feat = d_out;
   int ld_dfeat = ld_dout;
   const void* d_feat_amax = nullptr;
+  H16 d_feat_h{};
+  const gcbf_linear_desc& GL = net.gamma[net.n_gamma - 1];
+  const bool g_colsum = !skip_wgrad && GL.gW && GL.gb;
   if (net.n_head > 0) {
     void* slot = R.amax_slot();
     const float* d_hin; int ld_dhin; bool valid;
-    if (int rc = mlp_backward(R, net.head, net.n_head, ctx.head, d_out, ld_dout, true, nullptr, 0, false, nullptr, slot, skip_wgrad, &d_hin,
-                              &ld_dhin, &valid)) return rc;
+    // without a concatenated u_ref (CBF) the head's input gradient IS gamma's output gradient: emitted as a companion when both
+    // sides are tensor-core layers (with gamma's last bias gradient = its column sums)
+    const bool direct = net.head_extra_dim == 0;
+    if (int rc = mlp_backward(R, net.head, net.n_head, ctx.head, d_out, ld_dout, nullptr, false, true, nullptr, 0, false, nullptr, slot, skip_wgrad,
+                              direct ? &d_feat_h : nullptr, GL.K, g_colsum ? GL.gb : nullptr, &d_hin, &ld_dhin, &valid)) return rc;
     d_feat = d_hin; ld_dfeat = ld_dhin;         // the first F columns of d_hin (strided view when u_ref was concatenated)
     if (valid) d_feat_amax = slot;              // max over all of d_hin >= max over the d_feat columns: a valid (pow2) scale bound
   }
   const float* d_gin; int ld_dgin;
-  if (int rc = mlp_backward(R, net.gamma, net.n_gamma, ctx.gamma, d_feat, ld_dfeat, true, nullptr, 0, false, d_feat_amax, nullptr, skip_wgrad,
-                            &d_gin, &ld_dgin, nullptr)) return rc;
+  if (int rc = mlp_backward(R, net.gamma, net.n_gamma, ctx.gamma, d_feat, ld_dfeat, d_feat_h.buf ? &d_feat_h : nullptr, g_colsum, true, nullptr, 0,
+                            false, d_feat_amax, nullptr, skip_wgrad, nullptr, 0, nullptr, &d_gin, &ld_dgin, nullptr)) return rc;
   const float* d_gin_all = d_gin;
   int ld_dga = ld_dgin;
   if (row_index) {
@@ -435,11 +527,11 @@ int net_backward(Run& R, const gcbf_net_desc& net, const NetCtx& ctx, const int3
   // gate MLP backward; its input gradient is accumulated onto the aggregation's d_msg
   void* slot = R.amax_slot();
   bool valid = false;
-  if (int rc = mlp_backward(R, net.gate, net.n_gate, ctx.gate, d_gate, 1, true, d_msg, C, true, nullptr, slot, skip_wgrad, nullptr, nullptr,
-                            &valid)) return rc;
+  if (int rc = mlp_backward(R, net.gate, net.n_gate, ctx.gate, d_gate, 1, nullptr, false, true, d_msg, C, true, nullptr, slot, skip_wgrad, nullptr, 0,
+                            nullptr, nullptr, nullptr, &valid)) return rc;
   const float* d_ein; int ld_dein;
-  if (int rc = mlp_backward(R, net.phi, net.n_phi, ctx.phi, d_msg, C, d_edge_attr != nullptr, nullptr, 0, false, valid ? slot : nullptr, nullptr,
-                            skip_wgrad, &d_ein, &ld_dein, nullptr)) return rc;
+  if (int rc = mlp_backward(R, net.phi, net.n_phi, ctx.phi, d_msg, C, nullptr, false, d_edge_attr != nullptr, nullptr, 0, false,
+                            valid ? slot : nullptr, nullptr, skip_wgrad, nullptr, 0, nullptr, &d_ein, &ld_dein, nullptr)) return rc;
   if (d_edge_attr && !R.dry && E > 0) {
     CHAIN_CALL(gcbf_copy2d(d_ein + 2 * nd, ld_dein, d_edge_attr, net.edge_dim, E, net.edge_dim, R.st));
     R.launched(1);
@@ -515,7 +607,7 @@ size_t net_bwd_bytes(const gcbf_net_desc& net, int64_t E, int Nn, int rows, bool
   const int od = net.n_head ? net.head[net.n_head - 1].N : net.gamma[net.n_gamma - 1].N;
   if (net_forward(F, net, nullptr, nullptr, nullptr, nullptr, E, Nn, ri, rows, nullptr, &g_dummy_f, od, &ctx)) return 0;
   Run B(nullptr, 0, nullptr, true);
-  if (net_backward(B, net, ctx, nullptr, ri, nullptr, od, need_d_edge_attr ? &g_dummy_f : nullptr, skip_wgrad)) return 0;
+  if (net_backward(B, net, ctx, nullptr, ri, &g_dummy_f, od, need_d_edge_attr ? &g_dummy_f : nullptr, skip_wgrad)) return 0;
   return B.ws.off;
 }
 }}  // namespace gcbf::chain
@@ -570,7 +662,7 @@ static int mlp_fwd_run(Run& R, const gcbf_linear_desc* layers, int n, int refres
   if (int rc = sn_power_iter(R, all, n, ctx != nullptr, isg, us, vs)) return rc;
   if (refresh) { if (int rc = refresh_weight_companions(R, all, n)) return rc; }
   const float* y; int ldy;
-  return mlp_forward(R, layers, n, x, ldx, rows, nullptr, 0, isg, us, vs, ctx, out, ld_out, &y, &ldy, nullptr);
+  return mlp_forward(R, layers, n, x, ldx, rows, nullptr, nullptr, 0, isg, us, vs, ctx, out, ld_out, true, nullptr, &y, &ldy, nullptr);
 }
 
 extern "C" size_t gcbf_mlp_forward_workspace_bytes(const gcbf_linear_desc* layers, int n_layers, int rows, int save_ctx) {
@@ -589,7 +681,8 @@ extern "C" size_t gcbf_mlp_backward_workspace_bytes(const gcbf_linear_desc* laye
   static float dummy;
   if (mlp_fwd_run(F, layers, n_layers, 0, nullptr, layers[0].K, rows, &dummy, layers[n_layers - 1].N, &ctx)) return 0;
   Run B(nullptr, 0, nullptr, true);
-  if (mlp_backward(B, layers, n_layers, ctx, nullptr, layers[n_layers - 1].N, true, nullptr, 0, false, nullptr, nullptr, false, nullptr, nullptr, nullptr)) return 0;
+  if (mlp_backward(B, layers, n_layers, ctx, &g_dummy_f, layers[n_layers - 1].N, nullptr, false, true, nullptr, 0, false, nullptr, nullptr, false, nullptr, 0, nullptr,
+                   nullptr, nullptr, nullptr)) return 0;
   return B.ws.off + 1024;
 }
 
@@ -611,7 +704,7 @@ extern "C" int gcbf_mlp_backward(const gcbf_linear_desc* layers, int n_layers, c
   GCBF_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "gcbf_mlp_backward: workspace must be 256-byte aligned");
   Run R(workspace, workspace_bytes, as_stream(stream), false);
   const MlpCtx& c = *reinterpret_cast<const MlpCtx*>(ctx);
-  int rc = mlp_backward(R, layers, n_layers, c, d_out, ld_dout, d_x != nullptr, d_x, layers[0].K, false, nullptr, nullptr, skip_wgrad != 0, nullptr,
-                        nullptr, nullptr);
+  int rc = mlp_backward(R, layers, n_layers, c, d_out, ld_dout, nullptr, false, d_x != nullptr, d_x, layers[0].K, false, nullptr, nullptr,
+                        skip_wgrad != 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
   return R.finish(rc, "gcbf_mlp_backward");
 }

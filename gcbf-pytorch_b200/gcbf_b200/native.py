@@ -34,11 +34,11 @@ class NetDesc(ctypes.Structure):
 
 
 class NetCtx(ctypes.Structure):
-    _fields_ = [('opaque', c_uint64 * 160)]
+    _fields_ = [('opaque', c_uint64 * 208)]
 
 
 class MlpCtx(ctypes.Structure):
-    _fields_ = [('opaque', c_uint64 * 48)]
+    _fields_ = [('opaque', c_uint64 * 64)]
 
 
 class StepDesc(ctypes.Structure):
@@ -63,7 +63,13 @@ class StepOut(ctypes.Structure):
 
 
 class StepCtx(ctypes.Structure):
-    _fields_ = [('opaque', c_uint64 * 640)]
+    _fields_ = [('opaque', c_uint64 * 800)]
+
+
+class H16Desc(ctypes.Structure):
+    """mirror of `gcbf_h16`: fp16 [hi|lo] companion with a per-tensor (strides 0) or per-(128 x 256)-tile scale"""
+    _fields_ = [('buf', P), ('amax', P), ('ld', c_int32), ('rows', c_int32), ('cols', c_int32), ('amax_row_stride', c_int32),
+                ('amax_col_stride', c_int32), ('pad_', c_int32)]
 
 
 class TimeRec(ctypes.Structure):
@@ -86,6 +92,10 @@ SIGS = {
     'gcbf_step_relink': (c_int, [POINTER(StepDesc), POINTER(StepBatch), POINTER(StepCtx), P, c_size_t, POINTER(c_size_t),
                                  POINTER(StepOut), P, P]),
     'gcbf_step_backward': (c_int, [POINTER(StepDesc), POINTER(StepBatch), POINTER(StepCtx), POINTER(StepOut), P, P]),
+    'gcbf_linear_fwd_t': (c_int, [POINTER(H16Desc), POINTER(H16Desc), P, P, c_int, P, c_int, POINTER(H16Desc), P, c_int, c_int, c_int, P]),
+    'gcbf_linear_bwd_data_t': (c_int, [POINTER(H16Desc), POINTER(H16Desc), P, P, c_int, POINTER(H16Desc), P, c_int, c_int, POINTER(H16Desc), P, P,
+                                       c_int, c_int, c_int, P]),
+    'gcbf_linear_bwd_weight_t': (c_int, [POINTER(H16Desc), POINTER(H16Desc), P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'gcbf_launch_count': (c_longlong, [c_int]),
     'gcbf_timing_enable': (c_int, [c_int]),
     'gcbf_timing_collect': (c_int, [POINTER(TimeRec), c_int, POINTER(c_int)]),

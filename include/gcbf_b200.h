@@ -43,7 +43,7 @@ const char* gcbf_last_error(void);
 int gcbf_abi_version(void);
 /* sizeof() of ABI structure number `which` as the library was compiled (0 gcbf_env_cfg, 1 gcbf_linear_desc, 2 gcbf_net_desc,
  * 3 gcbf_step_desc, 4 gcbf_step_batch, 5 gcbf_step_out, 6 gcbf_net_ctx, 7 gcbf_mlp_ctx, 8 gcbf_step_ctx, 9 gcbf_time_rec,
- * 10 gcbf_sn_layer, 11 gcbf_split_desc; 0 for unknown): bindings check their mirrors against it */
+ * 10 gcbf_sn_layer, 11 gcbf_split_desc, 12 gcbf_h16; 0 for unknown): bindings check their mirrors against it */
 size_t gcbf_abi_struct_size(int which);
 /* 1 if the library was built with the tcgen05 (3xFP16) GEMM path compiled in, else 0 */
 int gcbf_has_tcgen05(void);
@@ -146,6 +146,29 @@ int gcbf_linear_bwd_data_h(const void* dZh, int lddzh, const void* dz_amax, cons
 int gcbf_linear_bwd_weight_h(const void* dZh, int lddzh, const void* dz_amax, const void* Xh, int ldxh,
                              const void* x_amax, const float* inv_sigma, float* dW, int lddw, int M, int N, int K,
                              int accumulate, void* stream);
+/* The general form of the three products (ABI v3): operands are `gcbf_h16` descriptors whose scale is either one word per tensor
+ * (amax strides 0, what gcbf_split_f16 makes) or one word per (128-row, 256-column) tile of the matrix (amax[rb * amax_row_stride +
+ * ct * amax_col_stride]) -- the format the EPILOGUES emit: a forward / data-grad launch can write its output directly as a tile-
+ * scaled companion (Yh / dXh, output width > 128), because every CTA knows the exact maximum of its own 128 x 256 tile.  That
+ * removes the amax + split passes (and the fp32 round trip through HBM) for every hidden activation / gradient between two
+ * tensor-core layers.  Y / dX may be NULL when only the companion is wanted.  data-grad extras: the ReLU mask can be read from
+ * the hi plane of the layer output's companion (relu_h; y > 0 <=> hi > 0), and `colsum` (optional) atomically accumulates the
+ * column sums of the masked output (= the bias gradient of the layer below).  Weight companions stay per-tensor. */
+typedef struct gcbf_h16 {
+  void* buf;                /* hi plane [rows][ld] halves, lo plane at buf + rows * ld halves */
+  void* amax;               /* uint32 float bits of max|x|: per tensor, or per tile */
+  int32_t ld, rows, cols;
+  int32_t amax_row_stride;  /* words between the rows of the tile-maxima array (0: per-tensor) */
+  int32_t amax_col_stride;  /* 1 for a tile-scaled companion, 0 per-tensor */
+  int32_t pad_;
+} gcbf_h16;
+int gcbf_linear_fwd_t(const gcbf_h16* X, const gcbf_h16* W, const float* bias, const float* inv_sigma, int act, float* Y, int ldy,
+                      const gcbf_h16* Yh, void* out_amax, int M, int N, int K, void* stream);
+int gcbf_linear_bwd_data_t(const gcbf_h16* dZ, const gcbf_h16* W, const float* inv_sigma, const float* relu_src, int ld_relu,
+                           const gcbf_h16* relu_h, float* dX, int lddx, int accumulate, const gcbf_h16* dXh, float* colsum,
+                           void* out_amax, int M, int N, int K, void* stream);
+int gcbf_linear_bwd_weight_t(const gcbf_h16* dZ, const gcbf_h16* X, const float* inv_sigma, float* dW, int lddw, int accumulate,
+                             int M, int N, int K, void* stream);
 /* dZ = dY * act'(Y) for the output activation (tanh: 1 - Y^2; relu: Y > 0).  In place allowed. */
 int gcbf_act_bwd(const float* dY, const float* Y, float* dZ, int64_t count, int act, void* stream);
 
@@ -304,7 +327,7 @@ typedef struct gcbf_net_desc {
 } gcbf_net_desc;
 
 /* what a forward saves for its backward: pointers into the forward's workspace (which must stay alive and untouched) */
-typedef struct gcbf_net_ctx { uint64_t opaque[160]; } gcbf_net_ctx;
+typedef struct gcbf_net_ctx { uint64_t opaque[208]; } gcbf_net_ctx;
 
 /* bytes a forward (save_ctx != 0: everything the backward reads is kept) / a backward needs for E edges, num_nodes nodes,
  * `rows` gamma rows (= num_nodes without row selection) */
@@ -322,7 +345,7 @@ int gcbf_net_forward(const gcbf_net_desc* net, const float* x, const float* edge
 int gcbf_net_backward(const gcbf_net_desc* net, const gcbf_net_ctx* ctx, const float* d_out, int ld_dout, float* d_edge_attr,
                       int skip_wgrad, void* workspace, size_t workspace_bytes, void* stream);
 /* a bare MLP (gcbf.nn.MLP.forward, mlp.py:44-47) through the same chain code */
-typedef struct gcbf_mlp_ctx { uint64_t opaque[48]; } gcbf_mlp_ctx;
+typedef struct gcbf_mlp_ctx { uint64_t opaque[64]; } gcbf_mlp_ctx;
 size_t gcbf_mlp_forward_workspace_bytes(const gcbf_linear_desc* layers, int n_layers, int rows, int save_ctx);
 size_t gcbf_mlp_backward_workspace_bytes(const gcbf_linear_desc* layers, int n_layers, int rows);
 int gcbf_mlp_forward(const gcbf_linear_desc* layers, int n_layers, int refresh_weights, const float* x, int ldx, int rows,
@@ -368,7 +391,7 @@ typedef struct gcbf_step_out {   /* device pointers into the workspaces, valid u
   int64_t* edge_index_new; int64_t num_edges_new;                                        /* re-linked graph [2, E'] */
 } gcbf_step_out;
 
-typedef struct gcbf_step_ctx { uint64_t opaque[640]; } gcbf_step_ctx;
+typedef struct gcbf_step_ctx { uint64_t opaque[800]; } gcbf_step_ctx;
 
 size_t gcbf_step_workspace_bytes(const gcbf_step_desc* d, const gcbf_step_batch* b);            /* workspace (forward + backward) */
 size_t gcbf_step_relink_workspace_bytes(const gcbf_step_desc* d, const gcbf_step_batch* b, int64_t num_edges_new);

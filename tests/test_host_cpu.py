@@ -352,7 +352,7 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     assert lib.gcbf_linear_fwd_h(args['Xh'], 64, None, args['Wh'], 64, ok_ptr, None, None, ok_ptr, 256, 512, 256, 64, 0, None, None) == -1
     assert lib.gcbf_linear_fwd_h(args['Xh'], 64, ok_ptr, args['Wh'], 64, ok_ptr, None, None, ok_ptr, 100, 512, 256, 64, 0, None, None) == -1
     assert lib.gcbf_linear_fwd_h(odd_ptr, 64, ok_ptr, args['Wh'], 64, ok_ptr, None, None, ok_ptr, 256, 512, 256, 64, 0, None, None) == -1
-    assert 'gcbf_linear_fwd_h' in err()
+    assert 'gcbf_linear_fwd_' in err()          # (the per-tensor entry points forward to the general gcbf_linear_fwd_t)
     assert lib.gcbf_linear_bwd_data_h(ok_ptr, 256, ok_ptr, ok_ptr, 64, ok_ptr, None, ok_ptr, 32, ok_ptr, 64, 512, 256, 64, 0, None, None) == -1   # ld_relu < K
     assert lib.gcbf_linear_bwd_weight_h(ok_ptr, 256, ok_ptr, ok_ptr, 62, ok_ptr, None, ok_ptr, 64, 512, 256, 64, 0, None) == -1    # pitch not a multiple of 8
     assert lib.gcbf_amax_split_batched(None, 3, None) == -1
@@ -368,7 +368,7 @@ def test_abi_struct_mirrors_and_workspace_queries_without_a_gpu():
     from gcbf_b200 import synth
     from gcbf_b200.synth import seeded_algo
     mirrors = [_C.EnvCfg, native.LinearDesc, native.NetDesc, native.StepDesc, native.StepBatch, native.StepOut, native.NetCtx,
-               native.MlpCtx, native.StepCtx, native.TimeRec, _C.SnLayer, _C.SplitDesc]
+               native.MlpCtx, native.StepCtx, native.TimeRec, _C.SnLayer, _C.SplitDesc, native.H16Desc]
     for i, m in enumerate(mirrors):
         assert ctypes.sizeof(m) == _C.lib().gcbf_abi_struct_size(i), m.__name__
     assert _C.lib().gcbf_abi_struct_size(99) == 0

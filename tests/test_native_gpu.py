@@ -61,8 +61,12 @@ def test_net_pass_matches_python_sequencing(env_name, n, obs, B, area, impl):
         assert torch.equal(x, y)
     if a['dea'].numel():
         assert rel(b['dea'], a['dea']) < 1e-5
-    for ga, gb in zip(a['gc'] + a['ga'], b['gc'] + b['ga']):
-        assert (gb - ga).norm() <= 1e-5 * ga.norm() + 1e-12, (ga.shape, rel(gb, ga))
+    # per tensor, relative to the whole net's gradient norm (the last gate bias has an exactly-zero gradient -- softmax is shift
+    # invariant -- so its entries are pure atomics-order noise)
+    for key in ('gc', 'ga'):
+        total = torch.sqrt(sum((g.double() ** 2).sum() for g in a[key]))
+        for ga, gb in zip(a[key], b[key]):
+            assert (gb.double() - ga.double()).norm() <= 1e-5 * ga.double().norm() + 1e-7 * total, (ga.shape, rel(gb, ga))
 
 
 @pytest.mark.parametrize('limit_lip', [False, True])
@@ -140,6 +144,6 @@ def test_step_workspace_grows_for_a_denser_relinked_graph():
 def test_abi_struct_mirrors_match_the_library():
     import ctypes
     mirrors = [_C.EnvCfg, native.LinearDesc, native.NetDesc, native.StepDesc, native.StepBatch, native.StepOut, native.NetCtx,
-               native.MlpCtx, native.StepCtx, native.TimeRec, _C.SnLayer, _C.SplitDesc]
+               native.MlpCtx, native.StepCtx, native.TimeRec, _C.SnLayer, _C.SplitDesc, native.H16Desc]
     for i, m in enumerate(mirrors):
         assert ctypes.sizeof(m) == _C.lib().gcbf_abi_struct_size(i), m.__name__
