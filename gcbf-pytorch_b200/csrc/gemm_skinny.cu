@@ -7,6 +7,8 @@
 //   dgrad : dX[M,K] = alpha * dZ[M,N] W[N,K]                 warp = 4 rows, lanes sweep N against W^T staged in smem,
 //                                                            shuffle-reduce the K sums
 //   wgrad : dW[N,K] += alpha * dZ^T X ; db[N] += colsum(dZ)  thread = column n, rows split over blockIdx.y
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace gcbf {
@@ -77,6 +79,101 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict
   if (amax_out) {   // max|Y| for the fp16 split of the next (tensor-core) layer; non-negative floats order like uints
     const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(ymax));
     if ((threadIdx.x & 31) == 0 && m) atomicMax(amax_out, m);
+  }
+}
+
+// The same layer writing its output directly as a tile-scaled fp16 [hi|lo] companion (the format the tensor-core epilogues emit,
+// gemm_tcgen05_f16.cu): a block owns one 128-row x 256-column tile; with K <= 16 an output costs 2*K flops, so the tile is computed
+// TWICE -- once for its exact max|y| (the tile's scale), once to convert and store -- instead of writing fp32, re-reading it for an
+// amax pass and again for a split pass (12 B/element of HBM traffic become 4).
+__device__ __forceinline__ uint32_t skinny_scale_bits(uint32_t amax_bits) {     // == th::scale_bits_from_amax
+  const int e = (int)((amax_bits >> 23) & 0xffu);
+  if (e == 0 || e == 255) return 0x3f800000u;
+  int se = 127 + 14 - (e - 127);
+  se = se < 2 ? 2 : (se > 252 ? 252 : se);
+  return (uint32_t)se << 23;
+}
+
+__global__ void __launch_bounds__(256) skinny_fwd_emit_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                                                              const float* __restrict__ bias, const float* __restrict__ alpha_p,
+                                                              __half* __restrict__ Yh, int ld_h, uint32_t* __restrict__ tile_amax,
+                                                              int amax_stride, int M, int N, int K, int act) {
+  __shared__ __align__(16) float xs[128][SK];
+  __shared__ uint32_t wmax[8];
+  const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;              // 64 column groups of 4 x 4 row groups of 32
+  const int n0 = blockIdx.x * 256 + cg * 4, m0 = blockIdx.y * 128;
+  const float alpha = alpha_p ? __ldg(alpha_p) : 1.f;
+  float w[4][SK], b[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int k = 0; k < SK; ++k) w[c][k] = (n0 + c < N && k < K) ? __ldg(W + (size_t)(n0 + c) * ldw + k) * alpha : 0.f;
+    b[c] = (n0 + c < N && bias) ? __ldg(bias + n0 + c) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 128 * SK; i += 256) {
+    const int r = i / SK, k = i % SK;
+    xs[r][k] = (m0 + r < M && k < K) ? X[(size_t)(m0 + r) * ldx + k] : 0.f;
+  }
+  __syncthreads();
+  const int rows = min(128, M - m0);
+  float s = 1.f;
+  const size_t plane = (size_t)M * ld_h;
+  const bool vec = (n0 + 4 <= N);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    float ymax = 0.f;
+    for (int r = rg * 32; r < min(rows, rg * 32 + 32); ++r) {
+      const float4* xr = reinterpret_cast<const float4*>(xs[r]);
+      float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < SK / 4; ++q) {
+        const float4 v = xr[q];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          y[c] = fmaf(v.x, w[c][4 * q], y[c]); y[c] = fmaf(v.y, w[c][4 * q + 1], y[c]);
+          y[c] = fmaf(v.z, w[c][4 * q + 2], y[c]); y[c] = fmaf(v.w, w[c][4 * q + 3], y[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        y[c] += b[c];
+        if (act == GCBF_ACT_RELU) y[c] = fmaxf(y[c], 0.f);
+        else if (act == GCBF_ACT_TANH) y[c] = tanhf(y[c]);
+        if (n0 + c >= N) y[c] = 0.f;
+      }
+      if (pass == 0) {
+        ymax = fmaxf(fmaxf(ymax, fmaxf(fabsf(y[0]), fabsf(y[1]))), fmaxf(fabsf(y[2]), fabsf(y[3])));
+      } else {
+        const float y0 = y[0] * s, y1 = y[1] * s, y2 = y[2] * s, y3 = y[3] * s;
+        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(__fsub_rn(y0, f01.x), __fsub_rn(y1, f01.y));
+        const __half2 l23 = __floats2half2_rn(__fsub_rn(y2, f23.x), __fsub_rn(y3, f23.y));
+        __half* d = Yh + (size_t)(m0 + r) * ld_h + n0;
+        if (vec) {
+          uint2 hi, lo;
+          hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+          lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(d) = hi;
+          *reinterpret_cast<uint2*>(d + plane) = lo;
+        } else {
+          const __half hs[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
+          const __half ls[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
+          for (int c = 0; c < 4; ++c)
+            if (n0 + c < N) { d[c] = hs[c]; d[plane + c] = ls[c]; }
+        }
+      }
+    }
+    if (pass == 0) {
+      const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(ymax));   // non-negative floats order like uints
+      if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+      __syncthreads();
+      uint32_t t = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t = max(t, wmax[i]);
+      s = __uint_as_float(skinny_scale_bits(t));
+      if (threadIdx.x == 0) tile_amax[(size_t)blockIdx.y * amax_stride + blockIdx.x] = t;
+    }
   }
 }
 
@@ -215,6 +312,14 @@ int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const fl
   const int vec_ok = ((ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) ? 1 : 0;
   skinny_fwd_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, rpb,
                                                                   amax_out, vec_ok);
+  GCBF_LAUNCH_OK();
+  return GCBF_OK;
+}
+
+int launch_skinny_fwd_emit(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, __half* Yh, int ld_h,
+                           uint32_t* tile_amax, int amax_stride, int M, int N, int K, int act, cudaStream_t st) {
+  skinny_fwd_emit_kernel<<<dim3(ceil_div(N, 256), ceil_div(M, 128)), 256, 0, st>>>(X, ldx, W, ldw, bias, inv_sigma, Yh, ld_h, tile_amax, amax_stride,
+                                                                                M, N, K, act);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }

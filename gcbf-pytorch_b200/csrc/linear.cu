@@ -1,5 +1,7 @@
 // C-ABI dispatch of the fp32 linear layers (K3): skinny-K stream kernels for in-features <= 16, otherwise the exact-fp32
 // SIMT tile kernel.  (Big layers run on the tensor cores through gcbf_linear_*_h, gemm_tcgen05_f16.cu.)  Reference op site: gcbf/nn/mlp.py:44-47 (nn.Linear + ReLU chain).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace gcbf {
@@ -13,6 +15,8 @@ int launch_simt_wgrad(const float* dZ, int lddz, const float* X, int ldx, const 
 bool skinny_supported(int K);
 int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
                       int ldy, int M, int N, int K, int act, uint32_t* amax_out, cudaStream_t st);
+int launch_skinny_fwd_emit(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, __half* Yh, int ld_h,
+                           uint32_t* tile_amax, int amax_stride, int M, int N, int K, int act, cudaStream_t st);
 bool tiny_supported(int N, int K);
 int launch_tiny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y, int ldy,
                     int M, int N, int K, int act, cudaStream_t st);
@@ -107,4 +111,18 @@ extern "C" int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X,
   }
   g_last_impl = 1;
   return launch_simt_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);
+}
+
+// The skinny-K forward (in-features <= 16: the first phi layer) writing its output as a tile-scaled fp16 companion only -- for a
+// tensor-core layer that follows (no fp32 copy, no amax / split pass).  Yh: tile-scaled descriptor (amax strides (ceil(N/256), 1)).
+extern "C" int gcbf_linear_fwd_emit(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, int act,
+                                    const gcbf_h16* Yh, int M, int N, int K, void* stream) {
+  GCBF_REQUIRE(M > 0 && N > 0 && K > 0 && skinny_supported(K) && ldx >= K && ldw >= K, "gcbf_linear_fwd_emit: bad sizes M=%d N=%d K=%d (K <= 16)", M, N, K);
+  GCBF_REQUIRE(X && W && Yh && Yh->buf && Yh->amax && Yh->rows == M && Yh->cols == N && Yh->ld >= N && (Yh->ld & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(Yh->buf) & 15) == 0 && Yh->amax_row_stride == ceil_div(N, 256) && Yh->amax_col_stride == 1,
+               "gcbf_linear_fwd_emit: companion descriptor");
+  GCBF_REQUIRE(act >= GCBF_ACT_NONE && act <= GCBF_ACT_TANH, "gcbf_linear_fwd_emit: act %d", act);
+  g_last_impl = 3;
+  return launch_skinny_fwd_emit(X, ldx, W, ldw, bias, inv_sigma, reinterpret_cast<__half*>(Yh->buf), Yh->ld, reinterpret_cast<uint32_t*>(Yh->amax),
+                                Yh->amax_row_stride, M, N, K, act, as_stream(stream));
 }

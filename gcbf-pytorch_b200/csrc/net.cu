@@ -176,7 +176,8 @@ int mlp_forward(Run& R, const gcbf_linear_desc* layers, int n, const float* x, i
     const bool lastl = (l == n - 1);
     const int nxt = !lastl ? layers[l + 1].N : next_width;
     const bool h = use_h(M, N, K) && M > 0;
-    const bool emit = h && can_emit(M, N, nxt) && (!lastl || out_h != nullptr);
+    const bool sk_emit = !h && !lastl && K <= 16 && M >= 64 && N >= 64 && cur && g_gemm_impl == 0 && can_emit(M, N, nxt);
+    const bool emit = sk_emit || (h && can_emit(M, N, nxt) && (!lastl || out_h != nullptr));
     const bool f32 = !emit || (lastl && need_f32_out);
     void* ya = (!emit && nxt > 0 && use_h(M, nxt, N)) ? R.amax_slot() : nullptr;
     float* dst = nullptr; int ldd = N;
@@ -193,6 +194,15 @@ int mlp_forward(Run& R, const gcbf_linear_desc* layers, int n, const float* x, i
         Timed t(R, 0, 2.0 * M * N * K, M, N, K);
         const gcbf_h16 X = h16_desc(cur_h), W = weight_desc(L), Y = h16_desc(yh);
         CHAIN_CALL(gcbf_linear_fwd_t(&X, &W, L.b, inv_sigma[l], L.act, dst, ldd, emit ? &Y : nullptr, ya, M, N, K, R.st));
+        R.launched(1);
+      }
+    } else if (sk_emit) {
+      // skinny-K layer in front of a tensor-core layer: companion only (each tile computed twice, nothing re-read)
+      yh = alloc_tiled(R, M, N);
+      if (!R.dry) {
+        Timed t(R, 3, 2.0 * M * N * K, M, N, K);
+        const gcbf_h16 Y = h16_desc(yh);
+        CHAIN_CALL(gcbf_linear_fwd_emit(cur, ldc, L.W, L.ldw, L.b, inv_sigma[l], L.act, &Y, M, N, K, R.st));
         R.launched(1);
       }
     } else {

@@ -96,6 +96,7 @@ SIGS = {
     'gcbf_linear_bwd_data_t': (c_int, [POINTER(H16Desc), POINTER(H16Desc), P, P, c_int, POINTER(H16Desc), P, c_int, c_int, POINTER(H16Desc), P, P,
                                        c_int, c_int, c_int, P]),
     'gcbf_linear_bwd_weight_t': (c_int, [POINTER(H16Desc), POINTER(H16Desc), P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'gcbf_linear_fwd_emit': (c_int, [P, c_int, P, c_int, P, P, c_int, POINTER(H16Desc), c_int, c_int, c_int, P]),
     'gcbf_launch_count': (c_longlong, [c_int]),
     'gcbf_timing_enable': (c_int, [c_int]),
     'gcbf_timing_collect': (c_int, [POINTER(TimeRec), c_int, POINTER(c_int)]),

@@ -169,6 +169,10 @@ int gcbf_linear_bwd_data_t(const gcbf_h16* dZ, const gcbf_h16* W, const float* i
                            void* out_amax, int M, int N, int K, void* stream);
 int gcbf_linear_bwd_weight_t(const gcbf_h16* dZ, const gcbf_h16* X, const float* inv_sigma, float* dW, int lddw, int accumulate,
                              int M, int N, int K, void* stream);
+/* the skinny-K fp32 forward (in-features <= 16: the first phi layer, gnn.py:31) writing ONLY the tile-scaled companion of its output
+ * (each 128 x 256 tile is computed twice: once for its exact maximum, once to convert and store) */
+int gcbf_linear_fwd_emit(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, int act,
+                         const gcbf_h16* Yh, int M, int N, int K, void* stream);
 /* dZ = dY * act'(Y) for the output activation (tanh: 1 - Y^2; relu: Y > 0).  In place allowed. */
 int gcbf_act_bwd(const float* dY, const float* Y, float* dZ, int64_t count, int act, void* stream);
 

@@ -134,3 +134,22 @@ def test_cpu_model_of_tile_scaled_products_matches_the_kernel():
                                                 _C.stream()), 'fwd')
     want = F16.gemm_tiled_a(x.abs(), W)
     assert torch.equal(out.cpu(), want)
+
+
+@pytest.mark.parametrize('M,N,K,act', [(5000, 2048, 13, 1), (300, 2048, 12, 1), (1000, 300, 14, 0), (129, 256, 16, 2)])
+def test_skinny_forward_emits_the_split_of_the_fp32_kernel_output(M, N, K, act):
+    """gcbf_linear_fwd_emit (first phi layer, in-features <= 16, companion only) against the fp32 skinny kernel + the CPU model of the
+    tile-scaled split: bit-exact (same FMA order; the tile maximum is computed from the very values that are converted)."""
+    g = _g(M + N + K)
+    x, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    xd, Wd, bd = x.to(DEV), W.to(DEV), b.to(DEV)
+    alpha = torch.tensor([0.9], device=DEV)
+    y = ops.linear_fwd(xd, Wd, bd, alpha, act)
+    assert _C.lib().gcbf_last_gemm_impl() == 3
+    yd, ybuf, yamax = tiled_buffers(M, N)
+    native.check(native.fn('gcbf_linear_fwd_emit')(_C.ptr(xd), K, _C.ptr(Wd), K, _C.ptr(bd), _C.ptr(alpha), act, ctypes.byref(yd), M, N, K,
+                                                   _C.stream()), 'gcbf_linear_fwd_emit')
+    torch.cuda.synchronize()
+    hi, lo, amax = F16.split_tiled(y.cpu())
+    assert torch.equal(yamax.view(torch.float32).cpu(), amax)
+    assert torch.equal(ybuf[0, :, :N].cpu(), hi) and torch.equal(ybuf[1, :, :N].cpu(), lo)
