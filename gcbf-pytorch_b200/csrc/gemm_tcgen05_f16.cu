@@ -72,6 +72,8 @@ struct EpiParams {
   int emit_h;
   uint32_t* out_tile_amax;     // [ceil(Mo/128)][out_amax_stride] float bits of the tile maxima
   int out_amax_stride;
+  int emit_direct;             // companion planes leave by 16-byte global stores from the registers instead of smem + bulk tensor stores
+  __half* out_hi; size_t out_plane; int ld_oh;   // (for emit_direct) hi plane, distance to the lo plane in halves, pitch
   float* colsum;               // optional: column sums of the (masked) output are atomically added here (bias gradient = colsum of dZ)
   int dbg;                     // GCBF_TC_DBG experiments: 1 = skip the global stores of the epilogue, 2 = no TMA stores
 };
@@ -441,6 +443,30 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             for (int g = 0; g < CH / 64; ++g) {
               const int col0 = n0 + chalf * CH + g * 64;
               if (col0 >= No) continue;                          // warp-uniform
+              if (ep.emit_direct && row_ok && col0 + 64 <= No) {
+                // 128 contiguous bytes per plane per thread-row: eight 16-byte stores, no staging, nothing to wait for
+#pragma unroll 1
+                for (int plane = 0; plane < 2; ++plane) {
+                  __half* drow = ep.out_hi + (size_t)plane * ep.out_plane + (size_t)row * ep.ld_oh + col0;
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const float y0 = acc[g * 64 + 8 * q + 2 * u], y1 = acc[g * 64 + 8 * q + 2 * u + 1];
+                      __half2 h = __floats2half2_rn(y0, y1);
+                      if (plane) {
+                        const float2 hf = __half22float2(h);
+                        h = __floats2half2_rn(__fsub_rn(y0, hf.x), __fsub_rn(y1, hf.y));
+                      }
+                      w[u] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(drow + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+                  }
+                }
+                continue;
+              }
+              if (ep.emit_direct && !row_ok) continue;           // (ragged column tails of valid rows go through the clipped bulk store)
 #pragma unroll 1
               for (int plane = 0; plane < 2; ++plane) {
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -761,6 +787,7 @@ static int g_dbg = -1;         // GCBF_TC_DBG experiment switches (read once)
 // number of MMAs accumulated before the chunk sum is promoted to registers with round-to-nearest.  4 k-blocks = 128 K-elements = 24 MMAs
 // per chunk (GCBF_TC_KCH=8 restores the 256-element chunks of round 1; measured on the shipped DubinsCar checkpoint: max|du| 1.0e-5 -> see DESIGN 5)
 static int g_kch = 4;
+static int g_emit_direct = 0;   // GCBF_EPI_STORE=direct: emitted companions leave by plain 16-byte stores (experiment)
 static bool g_two_cta = true;
 
 // companion operand as the GEMM sees it: plane [rows][cols]; K-major: rows = output index, cols = contraction;
@@ -805,6 +832,8 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
       if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output companion) failed (%d) M=%d N=%d ld=%d", (int)r, oh->rows, oh->cols, oh->ld_h); return GCBF_E_CUDA; }
     }
     ep.emit_h = 1;
+    ep.emit_direct = g_emit_direct;
+    ep.out_hi = oh->hi; ep.out_plane = (size_t)oh->rows * oh->ld_h; ep.ld_oh = oh->ld_h;
     ep.out_tile_amax = oh->tile_amax;
     ep.out_amax_stride = oh->amax_stride;
   }
@@ -864,6 +893,8 @@ static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo,
     g_two_cta = !(c2 && c2[0] == '0');
     const char* kc = getenv("GCBF_TC_KCH");
     if (kc && atoi(kc) >= 1 && atoi(kc) <= KCH_MAX) g_kch = atoi(kc);
+    const char* es = getenv("GCBF_EPI_STORE");
+    g_emit_direct = (es && es[0] == 'd') ? 1 : 0;
   }
   if ((ep.a_sr || ep.a_sc || ep.b_sr || ep.b_sc) && g_kch > 4) { set_error("tile-scaled operands need promotion chunks of <= 128 K-elements (GCBF_TC_KCH <= 4)"); return GCBF_E_UNSUPPORTED; }
   if (BN == 256 && g_two_cta) return launch_cg<256, A_MN, B_MN, 2>(A, B, C, ldc, Mo, No, Kc, splits, ep, oh, st);

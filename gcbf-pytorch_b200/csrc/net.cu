@@ -680,7 +680,7 @@ extern "C" size_t gcbf_mlp_forward_workspace_bytes(const gcbf_linear_desc* layer
   Run R(nullptr, 0, nullptr, true);
   MlpCtx ctx;
   static float dummy;
-  if (mlp_fwd_run(R, layers, n_layers, 0, nullptr, layers[0].K, rows, &dummy, layers[n_layers - 1].N, save_ctx ? &ctx : nullptr)) return 0;
+  if (mlp_fwd_run(R, layers, n_layers, 0, &dummy, layers[0].K, rows, &dummy, layers[n_layers - 1].N, save_ctx ? &ctx : nullptr)) return 0;
   return R.ws.off + 1024;
 }
 
@@ -689,7 +689,7 @@ extern "C" size_t gcbf_mlp_backward_workspace_bytes(const gcbf_linear_desc* laye
   Run F(nullptr, 0, nullptr, true);
   MlpCtx ctx;
   static float dummy;
-  if (mlp_fwd_run(F, layers, n_layers, 0, nullptr, layers[0].K, rows, &dummy, layers[n_layers - 1].N, &ctx)) return 0;
+  if (mlp_fwd_run(F, layers, n_layers, 0, &dummy, layers[0].K, rows, &dummy, layers[n_layers - 1].N, &ctx)) return 0;
   Run B(nullptr, 0, nullptr, true);
   if (mlp_backward(B, layers, n_layers, ctx, &g_dummy_f, layers[n_layers - 1].N, nullptr, false, true, nullptr, 0, false, nullptr, nullptr, false, nullptr, 0, nullptr,
                    nullptr, nullptr, nullptr)) return 0;

@@ -1,7 +1,13 @@
-"""The chain-level entry points (gcbf_net_forward / _backward, gcbf_mlp_*, gcbf_step_*: host sequencing inside the library,
+"""(Run with GCBF_EPI_H=0 the two sequencings use the very same kernels and the forward outputs are bit-identical; by default the
+library path lets the GEMM epilogues emit tile-scaled companions between tensor-core layers -- a different, slightly more accurate
+rounding of the same products -- so the comparison allows 2e-6.)
+
+The chain-level entry points (gcbf_net_forward / _backward, gcbf_mlp_*, gcbf_step_*: host sequencing inside the library,
 csrc/net.cu + csrc/step.cu) against the per-kernel Python sequencing of round 1 (ops.net_forward / net_backward, GCBF._train_step):
 same kernels in the same order, so outputs must agree to atomics-reordering noise.  (Parity against the ORACLE is in
 test_parity_gpu.py / test_fullsize_gpu.py, which run through the chain-level path by default.)"""
+import os
+
 import pytest
 import torch
 
@@ -18,6 +24,16 @@ def _setup(env_name, n, obs, B, area, seed):
     sb = synth.make_states(env_name, n, obs, B, area, seed)
     env, algo = seeded_algo(env_name, n, DEV, 0, {'num_obs': sb.num_obs, 'area_size': area})
     return sb, env, algo, product_batch(env, sb, DEV)
+
+
+EMIT = os.environ.get('GCBF_EPI_H', '1') != '0'
+GTOL = 3e-4 if EMIT else 1e-5        # gradients: a rounding-level ReLU flip moves a layer's gradient by ~1/sqrt(#units) of one row
+
+
+def _close(a, b):
+    if not EMIT:
+        return torch.equal(a, b)
+    return torch.allclose(a, b, rtol=0, atol=2e-6 * max(1.0, float(b.abs().max())))
 
 
 def rel(a, b):
@@ -56,17 +72,17 @@ def test_net_pass_matches_python_sequencing(env_name, n, obs, B, area, impl):
         ops.NATIVE = True
         ops.GEMM_IMPL = old
     a, b = outs
-    assert torch.equal(a['h'], b['h']) and torch.equal(a['u'], b['u'])          # forward: no atomics -> bit-identical
+    assert _close(a['h'], b['h']) and _close(a['u'], b['u'])          # forward: no atomics -> bit-identical without emission
     for x, y in zip(a['uv'], b['uv']):
         assert torch.equal(x, y)
     if a['dea'].numel():
-        assert rel(b['dea'], a['dea']) < 1e-5
+        assert rel(b['dea'], a['dea']) < GTOL
     # per tensor, relative to the whole net's gradient norm (the last gate bias has an exactly-zero gradient -- softmax is shift
     # invariant -- so its entries are pure atomics-order noise)
     for key in ('gc', 'ga'):
         total = torch.sqrt(sum((g.double() ** 2).sum() for g in a[key]))
         for ga, gb in zip(a[key], b[key]):
-            assert (gb.double() - ga.double()).norm() <= 1e-5 * ga.double().norm() + 1e-7 * total, (ga.shape, rel(gb, ga))
+            assert (gb.double() - ga.double()).norm() <= GTOL * ga.double().norm() + GTOL * 1e-2 * total, (ga.shape, rel(gb, ga))
 
 
 @pytest.mark.parametrize('limit_lip', [False, True])
@@ -85,10 +101,10 @@ def test_bare_mlp_matches_python_sequencing(limit_lip):
     finally:
         ops.NATIVE = True
     (ya, dxa, ga), (yb, dxb, gb) = outs
-    assert torch.equal(ya, yb)
-    assert rel(dxb, dxa) < 1e-5
+    assert _close(ya, yb)
+    assert rel(dxb, dxa) < GTOL
     for p, q in zip(ga, gb):
-        assert rel(q, p) < 1e-5
+        assert rel(q, p) < GTOL
 
 
 @pytest.mark.parametrize('two_streams', ['0', '1'])
@@ -117,14 +133,16 @@ def test_train_step_matches_python_sequencing(monkeypatch, env_name, n, obs, B, 
         ops.NATIVE = True
     a, b = outs
     assert torch.equal(a['ei'], b['ei']) and torch.equal(a['safe'], b['safe']) and torch.equal(a['unsafe'], b['unsafe'])
-    for k in ('h', 'u', 'hn', 'hnn', 'hdot'):
-        assert torch.equal(a[k].reshape(-1), b[k].reshape(-1)), k
-    assert torch.allclose(a['s'], b['s'], rtol=0, atol=1e-7) and abs(a['acc'] - b['acc']) < 1e-12
+    for k in ('h', 'u', 'hn', 'hnn'):
+        assert _close(a[k].reshape(-1), b[k].reshape(-1)), k
+    assert torch.allclose(a['hdot'], b['hdot'], rtol=0, atol=(2e-6 / 0.03 if EMIT else 0.0))
+    M = a['h'].numel()
+    assert torch.allclose(a['s'], b['s'], rtol=0, atol=2e-6 if EMIT else 1e-7) and abs(a['acc'] - b['acc']) <= (2.0 / M if EMIT else 1e-12)
     for x, y in zip(a['uv'], b['uv']):
         assert torch.equal(x, y)
-    assert a['g'].norm() > 0 and (a['g'] - b['g']).norm() <= 1e-5 * a['g'].norm()
+    assert a['g'].norm() > 0 and (a['g'] - b['g']).norm() <= (2e-2 if EMIT else 1e-5) * a['g'].norm()
     # clipped Adam's first step is +-lr per entry: entries whose gradient is rounding noise may flip, nothing moves further
-    assert ((a['w'] - b['w']).abs() > 1e-7).float().mean().item() < 0.02
+    assert ((a['w'] - b['w']).abs() > 1e-7).float().mean().item() < (0.10 if EMIT else 0.02)
 
 
 def test_step_workspace_grows_for_a_denser_relinked_graph():
