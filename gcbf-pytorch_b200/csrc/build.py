@@ -24,12 +24,13 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=True):
-    if not force and not needs_build():
+def build(force=False, verbose=True, extra_defs=(), target=None):
+    target = target or OUT
+    if not force and not needs_build() and target == OUT:
         return OUT
-    objdir = os.path.join(HERE, 'build')
+    objdir = os.path.join(HERE, 'build' if target == OUT else 'build_' + os.path.basename(target)[:-3])
     os.makedirs(objdir, exist_ok=True)
-    defs = []
+    defs = list(extra_defs)
     if os.path.exists(os.path.join(HERE, 'gemm_tcgen05_f16.cu')):
         defs.append('-DGCBF_WITH_TCGEN05')
     procs = []
@@ -47,10 +48,13 @@ def build(force=False, verbose=True):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    cmd = [NVCC, '-shared', '-o', OUT] + objs
+    cmd = [NVCC, '-shared', '-o', target] + objs
     subprocess.check_call(cmd)
-    return OUT
+    return target
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv))
+    if '--epi8' in sys.argv:      # experiment build: 8 promotion / epilogue warps (round-1 layout) -> load with GCBF_B200_LIB=...
+        print(build(force=True, extra_defs=['-DGCBF_EPI_WARPS=8'], target=OUT.replace('.so', '_epi8.so')))
+    else:
+        print(build(force='--force' in sys.argv))

@@ -18,7 +18,7 @@
 //
 // Kernel.  Persistent CTAs (grid = #SMs), warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor 2-D boxes into
 // swizzled shared memory), warp 1 = MMA issuer (one thread; 6 tcgen05.mma K16 per 32-wide k-block; accumulators
-// double-buffered in 512 TMEM columns), warps 2-9 = chunk promotion + epilogue (output through shared memory + bulk tensor
+// double-buffered in 512 TMEM columns), warps 2-17 = chunk promotion + epilogue (output through shared memory + bulk tensor
 // stores).  256-wide tiles run as CTA pairs (cta_group::2: a 256 x 256 tile per pair, each CTA stages half of B, 6 stages x
 // 32 KB); 128-wide tiles as single CTAs.  The tensor core's fp32 accumulator truncates on every MMA (tools/acc_probe.py), so
 // K is consumed in chunks of 256: each chunk accumulates in a fresh TMEM buffer and the epilogue warps add the chunk sums
@@ -42,8 +42,14 @@ constexpr int BM = 128;
 constexpr int BK = GCBF_TH_BK;         // K elements per k-block (= one smem stage): 32 (64-byte K-major rows) or 64 (128-byte rows)
 static_assert(BK == 32 || BK == 64, "BK must be 32 or 64");
 constexpr int UMMA_K = 16;             // fp16: 32 bytes of K per instruction
-constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 promotion / epilogue
-constexpr int EPI_WARP0 = 2;
+constexpr int EPI_WARP0 = 2;           // warp0 TMA, warp1 MMA, warps 2..17 promotion / epilogue
+#ifndef GCBF_EPI_WARPS
+#define GCBF_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = GCBF_EPI_WARPS;   // 16 = 4 TMEM lane quarters x 4 column quarters: 64 accumulator columns per thread.  (8 warps with 128
+                                       // columns each left the per-chunk TMEM drain latency-bound -- one tcgen05.ld in flight per warp -- and
+                                       // the epilogue register-bound at the 168-register cap: measured ~900 idle MMA cycles per chunk boundary)
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int KCH_MAX = 256 / BK;      // k-blocks accumulated inside the tensor core before promotion to registers: upper limit (256 K-elements)
 constexpr int MN_BOX = 64;             // MN-major operands: one TMA box = 64 MN elements (128 B, SWIZZLE_128B) x BK k-rows
 
@@ -96,10 +102,10 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CG;               // B rows (output columns) staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int OUT_STAGE_BYTES = 8 * 32 * 128;   // per epilogue warp: one 32 x 32 fp32 chunk of the output tile
-  static constexpr int STAGES_FIT = (232448 - OUT_STAGE_BYTES - 1024 - 256) / STAGE_BYTES;   // 227 KB per CTA
+  static constexpr int OUT_STAGE_BYTES = EPI_WARPS * 32 * 128;   // per epilogue warp: one 32 x 32 fp32 (or 32 x 64 fp16) box of the output tile
+  static constexpr int STAGES_FIT = (232448 - OUT_STAGE_BYTES - 1024 - 512) / STAGE_BYTES;   // 227 KB per CTA
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, tile-max exchange*/;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator (256 / 512 columns)
 };
 
@@ -137,14 +143,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   using K = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_stage = smem + K::STAGES * K::STAGE_BYTES;   // 8 x 4 KB, 1024-byte aligned (SWIZZLE_128B boxes)
+  uint8_t* out_stage = smem + K::STAGES * K::STAGE_BYTES;   // EPI_WARPS x 4 KB, 1024-byte aligned (SWIZZLE_128B boxes)
   uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + K::OUT_STAGE_BYTES);
   uint64_t* full = bars;                        // [STAGES]  TMA -> MMA
   uint64_t* empty = bars + K::STAGES;           // [STAGES]  MMA -> TMA
   uint64_t* tfull = bars + 2 * K::STAGES;       // [2]       MMA -> epilogue
   uint64_t* tempty = bars + 2 * K::STAGES + 2;  // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * K::STAGES + 4);
-  uint32_t* epi_red = tmem_slot + 2;            // [2][8] per-warp maxima of the current output tile (double-buffered across tiles)
+  uint32_t* epi_red = tmem_slot + 2;            // [2][EPI_WARPS] per-warp maxima of the current output tile (double-buffered across tiles)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb0 = blockIdx.y * kblocks_per_split;
@@ -164,7 +170,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     if (ep.tma_store) tma_prefetch_desc(&map_c);
     if (ep.emit_h) { tma_prefetch_desc(&map_oh); tma_prefetch_desc(&map_ol); }
     for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * CG); }   // one arrive per epilogue warp (of both CTAs)
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS * CG); }   // one arrive per epilogue warp (of both CTAs)
     fence_barrier_init();
   }
   if (warp == 1) {            // one warp (the same one in both CTAs of a pair) allocates TMEM and later frees it
@@ -241,8 +247,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
       }
     } else if (warp >= EPI_WARP0) {
-      // ===== promotion / epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
-      constexpr int CH = BN / 2;                               // columns owned by one thread
+      // ===== promotion / epilogue warps 2..17: TMEM lane quarter = warp % 4, column quarter = (warp - 2) / 4 =====
+      constexpr int CH = BN / (EPI_WARPS / 4);                 // columns owned by one thread
       constexpr int MODE = A_MN ? EPI_WGRAD : (B_MN ? EPI_DGRAD : EPI_FWD);   // the operand layouts identify the product
       const int lg = warp & 3;
       const int chalf = (warp - EPI_WARP0) >> 2;
@@ -270,12 +276,12 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           tcgen05_fence_after();
           const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + chalf * CH) + ((uint32_t)(lg * 32) << 16);
 #pragma unroll
-          for (int cc = 0; cc < CH / 32; ++cc) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(taddr + (uint32_t)(cc * 32), r);
+          for (int cc = 0; cc < CH / 16; ++cc) {               // 16 columns per load: the thread budget is 96 registers, 64 of them accumulators
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(taddr + (uint32_t)(cc * 16), r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[cc * 32 + j] = __fmaf_rn(__uint_as_float(r[j]), cs, acc[cc * 32 + j]);
+            for (int j = 0; j < 16; ++j) acc[cc * 16 + j] = __fmaf_rn(__uint_as_float(r[j]), cs, acc[cc * 16 + j]);
           }
           tcgen05_fence_before();
           __syncwarp();
@@ -368,15 +374,15 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             }
           }
         }
-        // ---- tile maximum (companion scale): 8 warps of this CTA own the 128 x BN tile
+        // ---- tile maximum (companion scale): the epilogue warps of this CTA own the 128 x BN tile
         float s_tile = 1.f, inv_s_tile = 1.f;
         if (MODE != EPI_WGRAD && ep.emit_h) {
           const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(tmax));   // non-negative floats order like uints
-          if (lane == 0) epi_red[tile_par * 8 + (warp - EPI_WARP0)] = wmax;
-          asm volatile("bar.sync 1, 256;" ::: "memory");                                 // the 8 epilogue warps only
+          if (lane == 0) epi_red[tile_par * EPI_WARPS + (warp - EPI_WARP0)] = wmax;
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");               // the epilogue warps only
           uint32_t m = 0;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) m = max(m, epi_red[tile_par * 8 + w]);
+          for (int w = 0; w < EPI_WARPS; ++w) m = max(m, epi_red[tile_par * EPI_WARPS + w]);
           tile_par ^= 1;
           s_tile = __uint_as_float(scale_bits_from_amax(m));
           inv_s_tile = __uint_as_float(inv_pow2_bits(scale_bits_from_amax(m)));

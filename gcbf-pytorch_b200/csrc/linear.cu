@@ -18,6 +18,13 @@ int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const fl
 int launch_skinny_fwd_emit(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, __half* Yh, int ld_h,
                            uint32_t* tile_amax, int amax_stride, int M, int N, int K, int act, cudaStream_t st);
 bool tiny_supported(int N, int K);
+bool fewrows_supported(int M, int N, int K);
+int launch_fewrows_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y, int ldy, int M,
+                       int N, int K, int act, cudaStream_t st);
+int launch_fewrows_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src, int ld_relu,
+                         float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
+int launch_fewrows_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw, float* db, int M, int N,
+                         int K, int accumulate, cudaStream_t st);
 int launch_tiny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y, int ldy,
                     int M, int N, int K, int act, cudaStream_t st);
 int launch_tiny_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src,
@@ -61,6 +68,9 @@ extern "C" int gcbf_linear_fwd(const float* X, int ldx, const float* W, int ldw,
   if (impl == 0 && tiny_supported(N, K)) {                         // N <= 32: row-streaming kernel
     g_last_impl = 4;
     rc = launch_tiny_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
+  } else if (impl == 0 && fewrows_supported(M, N, K)) {           // M <= 64: a stream over the weights, not a tile grid
+    g_last_impl = 5;
+    rc = launch_fewrows_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
   } else {
     g_last_impl = 1;
     rc = launch_simt_fwd(X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, st);
@@ -86,6 +96,10 @@ extern "C" int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, i
     g_last_impl = 4;
     return launch_tiny_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
   }
+  if (impl == 0 && fewrows_supported(M, K, N)) {
+    g_last_impl = 5;
+    return launch_fewrows_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
+  }
   g_last_impl = 1;
   return launch_simt_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
 }
@@ -108,6 +122,10 @@ extern "C" int gcbf_linear_bwd_weight(const float* dZ, int lddz, const float* X,
   if (impl == 0 && skinny_supported(K) && N >= 64 && M >= 64) {
     g_last_impl = 3;
     return launch_skinny_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);
+  }
+  if (impl == 0 && fewrows_supported(M, N, K)) {
+    g_last_impl = 5;
+    return launch_fewrows_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);
   }
   g_last_impl = 1;
   return launch_simt_wgrad(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, accumulate, st);

@@ -48,7 +48,8 @@ size_t gcbf_abi_struct_size(int which);
 /* 1 if the library was built with the tcgen05 (3xFP16) GEMM path compiled in, else 0 */
 int gcbf_has_tcgen05(void);
 /* which kernel the most recent gcbf_linear_* call on this thread launched: 1 = fp32 SIMT tile GEMM,
- * 3 = fp32 skinny-K stream kernel (in-features <= 16), 4 = row-streaming kernel (out-features <= 32).  (The tcgen05 path
+ * 3 = fp32 skinny-K stream kernel (in-features <= 16), 4 = row-streaming kernel (out-features <= 32), 5 = few-rows kernels
+ * (M <= 64: rollout-time single-graph passes stream the weights instead of tiling the output).  (The tcgen05 path
  * has its own entry points, gcbf_linear_*_h.) */
 int gcbf_last_gemm_impl(void);
 

@@ -620,3 +620,36 @@ def _net_backward_check(algo, data, tol):
 
 def rel_err(a, b):
     return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-300)).item()
+
+
+@pytest.mark.parametrize('M,N,K', [(16, 2048, 2048), (44, 2048, 260), (1, 512, 1024), (64, 128, 32), (45, 256, 2048), (16, 1024, 1027), (33, 70, 130)])
+def test_linear_few_rows(M, N, K):
+    """M <= 64 (rollout-time single-graph passes, config C1): weight-streaming kernels (gemm_fewrows.cu) instead of a 128 x 128 tile
+    grid; exact fp32 FFMA, forward with fused bias / activation, data-grad with ReLU mask and accumulate, weight-grad + bias grad."""
+    g = _g(M + 3 * N + K)
+    x, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, generator=g)
+    dz, rs = torch.randn(M, N, generator=g), torch.randn(M, K, generator=g)
+    xd, Wd, bd, dzd, rsd = x.to(DEV), W.to(DEV), b.to(DEV), dz.to(DEV), rs.to(DEV)
+    alpha = torch.tensor([1.2], device=DEV)
+    assert ops.GEMM_IMPL == 0 and not ops.use_h(M, N, K)
+    am = torch.zeros(1, device=DEV, dtype=torch.int32)
+    y = ops.linear_fwd(xd, Wd, bd, alpha, ops.ACT_RELU, out_amax=am)
+    assert _C.lib().gcbf_last_gemm_impl() == 5
+    assert am.view(torch.float32).item() == y.abs().max().item()
+    dx = ops.linear_bwd_data(dzd, Wd, alpha, rsd)
+    assert _C.lib().gcbf_last_gemm_impl() == 5
+    dx_acc = torch.ones(M, K, device=DEV)
+    ops.linear_bwd_data(dzd, Wd, None, None, out=dx_acc, accumulate=True)
+    dW, db = ops.linear_bwd_weight(dzd, xd, alpha)
+    assert _C.lib().gcbf_last_gemm_impl() == 5
+    dW_acc = torch.ones(N, K, device=DEV)
+    db_acc = torch.ones(N, device=DEV)
+    ops.linear_bwd_weight(dzd, xd, None, out_w=dW_acc, out_b=db_acc)
+    x64, W64, dz64 = xd.double(), Wd.double(), dzd.double()
+    e = lambda a, r: ((a.double() - r).abs().max() / r.abs().max()).item()
+    assert e(y, torch.relu(1.2 * (x64 @ W64.t()) + bd.double())) < 2e-6
+    assert e(dx, 1.2 * (dz64 @ W64) * (rsd > 0)) < 2e-6
+    assert e(dx_acc, dz64 @ W64 + 1) < 2e-6
+    assert e(dW, 1.2 * (dz64.t() @ x64)) < 2e-6
+    assert e(dW_acc, dz64.t() @ x64 + 1) < 2e-6
+    assert e(db, dz64.sum(0)) < 1e-5 and e(db_acc, dz64.sum(0) + 1) < 1e-5
