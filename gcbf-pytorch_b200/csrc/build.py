@@ -54,7 +54,7 @@ def build(force=False, verbose=True, extra_defs=(), target=None):
 
 
 if __name__ == '__main__':
-    if '--epi8' in sys.argv:      # experiment build: 8 promotion / epilogue warps (round-1 layout) -> load with GCBF_B200_LIB=...
-        print(build(force=True, extra_defs=['-DGCBF_EPI_WARPS=8'], target=OUT.replace('.so', '_epi8.so')))
+    if '--epi16' in sys.argv:     # experiment build: 16 promotion / epilogue warps (measured slower) -> load with GCBF_B200_LIB=...
+        print(build(force=True, extra_defs=['-DGCBF_EPI_WARPS=16'], target=OUT.replace('.so', '_epi16.so')))
     else:
         print(build(force='--force' in sys.argv))

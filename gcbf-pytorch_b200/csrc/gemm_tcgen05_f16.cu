@@ -44,11 +44,11 @@ static_assert(BK == 32 || BK == 64, "BK must be 32 or 64");
 constexpr int UMMA_K = 16;             // fp16: 32 bytes of K per instruction
 constexpr int EPI_WARP0 = 2;           // warp0 TMA, warp1 MMA, warps 2..17 promotion / epilogue
 #ifndef GCBF_EPI_WARPS
-#define GCBF_EPI_WARPS 16
+#define GCBF_EPI_WARPS 8
 #endif
-constexpr int EPI_WARPS = GCBF_EPI_WARPS;   // 16 = 4 TMEM lane quarters x 4 column quarters: 64 accumulator columns per thread.  (8 warps with 128
-                                       // columns each left the per-chunk TMEM drain latency-bound -- one tcgen05.ld in flight per warp -- and
-                                       // the epilogue register-bound at the 168-register cap: measured ~900 idle MMA cycles per chunk boundary)
+constexpr int EPI_WARPS = GCBF_EPI_WARPS;   // 8 = 4 TMEM lane quarters x 2 column halves: 128 accumulator columns per thread.  (16 warps with 64
+                                       // columns each were measured: 96-register cap -> the promotion loop spills, 5 instead of 6 smem stages:
+                                       // the 206 k-row forward went from 3.79 to 4.91 ms; `build.py --epi16` keeps that build for comparison)
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int KCH_MAX = 256 / BK;      // k-blocks accumulated inside the tensor core before promotion to registers: upper limit (256 K-elements)
 constexpr int MN_BOX = 64;             // MN-major operands: one TMA box = 64 MN elements (128 B, SWIZZLE_128B) x BK k-rows
@@ -134,7 +134,9 @@ __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* map, 
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG>
+// EMIT: the instantiation that can write the output as a tile-scaled companion / accumulate its column sums (kept out of the plain
+// instantiation: the extra code costs registers the 128-value accumulator row of every epilogue thread needs)
+template <int BN, bool A_MN, bool B_MN, int CG, bool EMIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -168,7 +170,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     tma_prefetch_desc(&map_b_hi);
     tma_prefetch_desc(&map_b_lo);
     if (ep.tma_store) tma_prefetch_desc(&map_c);
-    if (ep.emit_h) { tma_prefetch_desc(&map_oh); tma_prefetch_desc(&map_ol); }
+    if (EMIT && ep.emit_h) { tma_prefetch_desc(&map_oh); tma_prefetch_desc(&map_ol); }
     for (int s = 0; s < K::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS * CG); }   // one arrive per epilogue warp (of both CTAs)
     fence_barrier_init();
@@ -292,7 +294,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const int row = m0 + lg * 32 + lane;
         const bool row_ok = row < Mo;
         const uint32_t my_stage = smem_u32(out_stage + (warp - EPI_WARP0) * 4096);
-        const bool need_clean = ep.emit_h || ep.colsum || ep.amax_out;     // out-of-range entries must read as exact zeros
+        const bool need_clean = (EMIT && (ep.emit_h || ep.colsum)) || ep.amax_out;     // out-of-range entries must read as exact zeros
         // ---- pass 1: finish the values in place: alpha, bias, activation / ReLU mask
         float tmax = 0.f;
 #pragma unroll
@@ -376,7 +378,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
         // ---- tile maximum (companion scale): the epilogue warps of this CTA own the 128 x BN tile
         float s_tile = 1.f, inv_s_tile = 1.f;
-        if (MODE != EPI_WGRAD && ep.emit_h) {
+        if (EMIT && MODE != EPI_WGRAD && ep.emit_h) {
           const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(tmax));   // non-negative floats order like uints
           if (lane == 0) epi_red[tile_par * EPI_WARPS + (warp - EPI_WARP0)] = wmax;
           asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");               // the epilogue warps only
@@ -439,7 +441,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           }
         }
         if (ep.amax_out && !ep.accumulate) out_max = fmaxf(out_max, tmax);
-        if (MODE != EPI_WGRAD && ep.emit_h) {
+        if (EMIT && MODE != EPI_WGRAD && ep.emit_h) {
           // the companion of this warp's 32 x CH block: per 64-column group one 32 x 64 fp16 box per plane (128-byte rows) through
           // the warp's shared-memory stage and a bulk tensor store; hi = fp16(y s), lo = fp16(y s - hi) as in split_h4_kernel
           if constexpr (CH >= 64) {
@@ -508,7 +510,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             }
           }
         }
-        if (MODE == EPI_DGRAD && ep.colsum) {
+        if (EMIT && MODE == EPI_DGRAD && ep.colsum) {
           // column sums over this warp's 32 rows (the bias gradient of the layer below = colsum of dZ): each 32 x 32 chunk goes
           // through the warp's shared-memory stage (same swizzled layout as the fp32 output boxes), lane j adds up column j, one
           // atomic per column per warp.  (A shuffle butterfly needs ~60 more live registers next to the 128 accumulators.)
@@ -537,7 +539,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           }
         }
       }
-      if ((ep.tma_store || ep.emit_h) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if ((ep.tma_store || (EMIT && ep.emit_h)) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       if (ep.amax_out) {
         const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(out_max));   // non-negative floats order like uints
         if (lane == 0 && m) atomicMax(ep.amax_out, m);
@@ -807,7 +809,7 @@ struct OutH {
   __half* hi; int rows; int cols; int ld_h; uint32_t* tile_amax; int amax_stride;
 };
 
-template <int BN, bool A_MN, bool B_MN, int CG>
+template <int BN, bool A_MN, bool B_MN, int CG, bool EMIT>
 static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int Mo, int No, int Kc, int splits, EpiParams ep,
                      const OutH* oh, cudaStream_t st) {
   using K = Cfg<BN, CG>;
@@ -858,7 +860,7 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    GCBF_CUDA_OK(cudaFuncSetAttribute(gemm_h_kernel<BN, A_MN, B_MN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    GCBF_CUDA_OK(cudaFuncSetAttribute(gemm_h_kernel<BN, A_MN, B_MN, CG, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles_m = ceil_div(Mo, BM * CG), tiles_n = ceil_div(No, BN);   // CG == 2: 256-row pair tiles
@@ -883,7 +885,7 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CG == 2) ? 1 : 0;
-  GCBF_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_h_kernel<BN, A_MN, B_MN, CG>, mah, mal, mbh, mbl, mc, moh, mol, C, ldc, Mo, No, tiles_m, tiles_n, kps,
+  GCBF_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_h_kernel<BN, A_MN, B_MN, CG, EMIT>, mah, mal, mbh, mbl, mc, moh, mol, C, ldc, Mo, No, tiles_m, tiles_n, kps,
                                   kblocks, g_kch, ep));
   return GCBF_OK;
 }
@@ -903,8 +905,15 @@ static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo,
     g_emit_direct = (es && es[0] == 'd') ? 1 : 0;
   }
   if ((ep.a_sr || ep.a_sc || ep.b_sr || ep.b_sc) && g_kch > 4) { set_error("tile-scaled operands need promotion chunks of <= 128 K-elements (GCBF_TC_KCH <= 4)"); return GCBF_E_UNSUPPORTED; }
-  if (BN == 256 && g_two_cta) return launch_cg<256, A_MN, B_MN, 2>(A, B, C, ldc, Mo, No, Kc, splits, ep, oh, st);
-  return launch_cg<BN, A_MN, B_MN, 1>(A, B, C, ldc, Mo, No, Kc, splits, ep, oh, st);
+  if constexpr (BN == 256 && !A_MN) {
+    if (oh || ep.colsum) {
+      if (g_two_cta) return launch_cg<256, A_MN, B_MN, 2, true>(A, B, C, ldc, Mo, No, Kc, splits, ep, oh, st);
+      return launch_cg<256, A_MN, B_MN, 1, true>(A, B, C, ldc, Mo, No, Kc, splits, ep, oh, st);
+    }
+  }
+  if (oh || ep.colsum) { set_error("companion emission / column sums need a 256-wide forward or data-grad launch"); return GCBF_E_UNSUPPORTED; }
+  if (BN == 256 && g_two_cta) return launch_cg<256, A_MN, B_MN, 2, false>(A, B, C, ldc, Mo, No, Kc, splits, ep, nullptr, st);
+  return launch_cg<BN, A_MN, B_MN, 1, false>(A, B, C, ldc, Mo, No, Kc, splits, ep, nullptr, st);
 }
 
 static int check_plane(const void* p, int ld_h, const char* what) {

@@ -166,7 +166,7 @@ static int step_relink(Run& R, const gcbf_step_desc& d, const gcbf_step_batch& b
 
 // ---- backward ----------------------------------------------------------------------------------------------------------------
 static int step_backward(Run& R, const gcbf_step_desc& d, const gcbf_step_batch& b, StepCtx* c, cudaStream_t main, cudaStream_t side,
-                         HostRes* hr) {
+                         HostRes* hr, void* const* events) {
   const int M = b.num_agents_total, Nn = b.num_nodes, E = (int)b.num_edges, a = d.action_dim, s = d.state_dim, ed = d.cbf.edge_dim;
   const bool two = side != nullptr && side != main && !R.dry;
   R.st = main;
@@ -197,12 +197,16 @@ static int step_backward(Run& R, const gcbf_step_desc& d, const gcbf_step_batch&
   if (two) { CHAIN_CUDA(cudaEventRecord(hr->dact_ready, main)); }
   const size_t after2 = R.ws.off;
   R.ws.off = mark;
-  if (int rc = net_backward(R, d.cbf, c->c1, b.rowptr, b.row_index, d_h, 1, nullptr, false)) return rc;    // h -> cbf params
+  // (events: the gamma + head gradients of a net are final once its LAST pass is through gamma -- callers start that range's
+  // all-reduce there, while the E-row phi / gate backward still runs)
+  if (int rc = net_backward(R, d.cbf, c->c1, b.rowptr, b.row_index, d_h, 1, nullptr, false, (events && !R.dry) ? (cudaEvent_t)events[0] : nullptr)) return rc;    // h -> cbf params
+  if (events && !R.dry) CHAIN_CUDA(cudaEventRecord((cudaEvent_t)events[1], main));
   const size_t after1 = R.ws.off;
   R.ws.off = after1 > after2 ? after1 : after2;
   // the actor's backward only needs d_act: on the side stream it overlaps the second CBF backward
   if (two) { CHAIN_CUDA(cudaStreamWaitEvent(side, hr->dact_ready, 0)); R.st = side; }
-  if (int rc = net_backward(R, d.actor, c->ca, b.rowptr, b.row_index, d_act, a, nullptr, false)) return rc;
+  if (int rc = net_backward(R, d.actor, c->ca, b.rowptr, b.row_index, d_act, a, nullptr, false, (events && !R.dry) ? (cudaEvent_t)events[2] : nullptr)) return rc;
+  if (events && !R.dry) CHAIN_CUDA(cudaEventRecord((cudaEvent_t)events[3], R.st));
   if (two) { CHAIN_CUDA(cudaEventRecord(hr->side_done, side)); CHAIN_CUDA(cudaStreamWaitEvent(main, hr->side_done, 0)); }
   R.st = main;
   return 0;
@@ -225,7 +229,7 @@ extern "C" size_t gcbf_step_workspace_bytes(const gcbf_step_desc* d, const gcbf_
   StepCtx c;
   memset(&c, 0, sizeof(c));
   if (step_forward(R, *d, *b, &c, nullptr, nullptr, nullptr)) return 0;
-  if (step_backward(R, *d, *b, &c, nullptr, nullptr, nullptr)) return 0;
+  if (step_backward(R, *d, *b, &c, nullptr, nullptr, nullptr, nullptr)) return 0;
   return R.ws.off + 4096;
 }
 
@@ -286,8 +290,8 @@ extern "C" int gcbf_step_relink(const gcbf_step_desc* d, const gcbf_step_batch* 
   return R.finish(rc, "gcbf_step_relink");
 }
 
-extern "C" int gcbf_step_backward(const gcbf_step_desc* d, const gcbf_step_batch* b, gcbf_step_ctx* ctx, gcbf_step_out* out, void* stream,
-                                  void* side_stream) {
+extern "C" int gcbf_step_backward(const gcbf_step_desc* d, const gcbf_step_batch* b, gcbf_step_ctx* ctx, gcbf_step_out* out, void* const* events,
+                                  void* stream, void* side_stream) {
   if (int rc = check_step(d, b, "gcbf_step_backward")) return rc;
   GCBF_REQUIRE(ctx && out, "gcbf_step_backward: bad arguments");
   StepCtx* c = reinterpret_cast<StepCtx*>(ctx);
@@ -296,7 +300,7 @@ extern "C" int gcbf_step_backward(const gcbf_step_desc* d, const gcbf_step_batch
   if (int rc = host_res(&hr)) return rc;
   Run R(c->ws_base, c->ws_cap, as_stream(stream), false);
   R.ws.off = c->off_after_forward;
-  int rc = step_backward(R, *d, *b, c, as_stream(stream), as_stream(side_stream), hr);
+  int rc = step_backward(R, *d, *b, c, as_stream(stream), as_stream(side_stream), hr, events);
   c->phase = 4;
   return R.finish(rc, "gcbf_step_backward");
 }

@@ -70,6 +70,16 @@ class _FlatBucket:
             p.grad = self.grad[off:off + n].view(p.shape)
             off += n
         self.params = params
+        # where the [gamma + head] parameters of each net start (parameters() order: gate_nn, phi, gamma, head): that tail of a
+        # net's range is final before the E-row phi / gate backward has run, so its all-reduce can start early
+        self.tail_start = []
+        for m, (lo, hi) in zip(modules, self.ranges):
+            off, tail = lo, hi
+            for name, p_ in m.named_parameters():
+                if '.gamma.' in name and tail == hi:
+                    tail = off
+                off += p_.numel()
+            self.tail_start.append(tail)
         self.sumsq = torch.zeros(len(modules), device=device, dtype=torch.float64)
         self.step = 0
 
@@ -337,8 +347,6 @@ class GCBF(Algorithm):
         native.check(rc, 'gcbf_step_relink')
         partial = native.view(ws, out.partial, (16,), torch.float64)
         red.sum_(partial)                                                # global counts => global masked means
-        native.check(native.fn('gcbf_step_backward')(ctypes.byref(d), ctypes.byref(b), ctypes.byref(ctx), ctypes.byref(out), main, side),
-                     'gcbf_step_backward')
         a_dim = self.action_dim
         En = int(out.num_edges_new)
         res = dict(scalars=native.view(ws, out.scalars, (8,), torch.float32), h=native.view(ws, out.h, (M, 1), torch.float32),
@@ -349,17 +357,55 @@ class GCBF(Algorithm):
                    edge_index_new=(native.view(ws2, out.edge_index_new, (2, En), torch.int64) if En else
                                    torch.empty(2, 0, device=dev, dtype=torch.int64)),
                    hdot=native.view(ws, out.hdot, (M,), torch.float32))
-        if compute_acc_h_dot:                                            # gcbf.py:209 (M x M broadcast mean)
-            cnt = torch.empty(1, device=dev, dtype=torch.int64)
-            sizes = red.sizes(M)
-            hdot_all = red.gather_cat(res['hdot'], sizes)
-            _C.call('gcbf_pair_count', _C.ptr(hdot_all), hdot_all.numel(), _C.ptr(res['h']), M, float(self.params['alpha']), _C.ptr(cnt))
-            red.sum_(cnt)
-            res['acc_h_dot'] = cnt.to(torch.float64) / float(sum(sizes)) / float(sum(sizes))
-        red.sum_(bucket.grad)                                            # the ONE gradient collective (K9)
+        # data-parallel: everything that is not on the critical path of the backward goes to a communication stream -- the
+        # h_dot gather + pair count of `acc/derivative` (needs only the forward's outputs) and the gradient all-reduces, each started
+        # as soon as its range of the flat bucket is final (events recorded inside gcbf_step_backward)
+        overlap = red.world > 1 and dev.type == 'cuda' and os.environ.get('GCBF_OVERLAP_COMM', '1') != '0'
+        comm, events, ev_arr = None, None, None
+        if overlap:
+            comm, events = self._comm_resources(dev)
+            ev_arr = (ctypes.c_void_p * 4)(*[e.cuda_event for e in events])
+            comm.wait_stream(torch.cuda.current_stream(dev))             # partial sums reduced, h / h_dot final
+            if compute_acc_h_dot:
+                with torch.cuda.stream(comm):
+                    res['acc_h_dot'] = self._acc_h_dot(red, res['hdot'], res['h'], M, dev)
+        native.check(native.fn('gcbf_step_backward')(ctypes.byref(d), ctypes.byref(b), ctypes.byref(ctx), ctypes.byref(out), ev_arr, main, side),
+                     'gcbf_step_backward')
+        if overlap:
+            (c_lo, c_hi), (a_lo, a_hi) = bucket.ranges
+            c_tail, a_tail = bucket.tail_start
+            with torch.cuda.stream(comm):
+                for ev, lo, hi in ((events[0], c_tail, c_hi), (events[2], a_tail, a_hi), (events[1], c_lo, c_tail), (events[3], a_lo, a_tail)):
+                    comm.wait_event(ev)
+                    red.sum_(bucket.grad[lo:hi])
+            torch.cuda.current_stream(dev).wait_stream(comm)
+        else:
+            if compute_acc_h_dot:                                        # gcbf.py:209 (M x M broadcast mean)
+                res['acc_h_dot'] = self._acc_h_dot(red, res['hdot'], res['h'], M, dev)
+            red.sum_(bucket.grad)                                        # the ONE gradient collective (K9)
         if apply_optim:
             self.optim_step()
         return res
+
+    def _acc_h_dot(self, red, hdot, h, M: int, dev):
+        """mean over all (i, j) of [h_dot_j + alpha h_i >= 0] (the M x M broadcast of gcbf.py:209) over the GLOBAL agent set: the
+        per-rank h_dot vectors are gathered (unequal shards allowed), every rank counts its rows, the counts are summed."""
+        cnt = torch.empty(1, device=dev, dtype=torch.int64)
+        sizes = red.sizes(M)
+        hdot_all = red.gather_cat(hdot, sizes)
+        _C.call('gcbf_pair_count', _C.ptr(hdot_all), hdot_all.numel(), _C.ptr(h), M, float(self.params['alpha']), _C.ptr(cnt))
+        red.sum_(cnt)
+        return cnt.to(torch.float64) / float(sum(sizes)) / float(sum(sizes))
+
+    def _comm_resources(self, dev):
+        r = getattr(self, '_comm', None)
+        if r is None or r[0].device != dev:
+            comm = torch.cuda.Stream(device=dev)
+            events = [torch.cuda.Event() for _ in range(4)]
+            for e in events:
+                e.record()                                               # materialise the cudaEvent_t handles
+            r = self._comm = (comm, events)
+        return r
 
     def optim_step(self):
         """clip_grad_norm_(1e-3) per net + Adam (gcbf.py:223-226), fused, on the flat bucket."""

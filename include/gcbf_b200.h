@@ -404,8 +404,10 @@ int gcbf_step_forward(const gcbf_step_desc* d, const gcbf_step_batch* b, void* w
                       gcbf_step_ctx* ctx, gcbf_step_out* out, void* stream, void* side_stream /* NULL: single stream */);
 int gcbf_step_relink(const gcbf_step_desc* d, const gcbf_step_batch* b, gcbf_step_ctx* ctx, void* workspace2,
                      size_t workspace2_bytes, size_t* needed_bytes, gcbf_step_out* out, void* stream, void* side_stream);
-int gcbf_step_backward(const gcbf_step_desc* d, const gcbf_step_batch* b, gcbf_step_ctx* ctx, gcbf_step_out* out, void* stream,
-                       void* side_stream);
+/* events (optional, 4 cudaEvent_t): recorded when a gradient range is final, so that a data-parallel caller can start its all-reduce
+ * while the rest of the backward still runs: [0] cbf gamma + head, [1] all of cbf, [2] actor gamma + head, [3] all of actor */
+int gcbf_step_backward(const gcbf_step_desc* d, const gcbf_step_batch* b, gcbf_step_ctx* ctx, gcbf_step_out* out, void* const* events,
+                       void* stream, void* side_stream);
 
 /* instrumentation (bench.py): kernels launched by the chain-level calls since the last reset, and optional CUDA-event timing of
  * every linear-layer launch (kind 0 forward / 1 data-grad / 2 weight-grad on the tensor cores, 3 fp32 linear kernels, 4 operand

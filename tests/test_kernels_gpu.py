@@ -637,7 +637,7 @@ def test_linear_few_rows(M, N, K):
     assert _C.lib().gcbf_last_gemm_impl() == 5
     assert am.view(torch.float32).item() == y.abs().max().item()
     dx = ops.linear_bwd_data(dzd, Wd, alpha, rsd)
-    assert _C.lib().gcbf_last_gemm_impl() == 5
+    assert _C.lib().gcbf_last_gemm_impl() == (5 if K >= 64 and N >= 32 else 1)      # (output width K, contraction N)
     dx_acc = torch.ones(M, K, device=DEV)
     ops.linear_bwd_data(dzd, Wd, None, None, out=dx_acc, accumulate=True)
     dW, db = ops.linear_bwd_weight(dzd, xd, alpha)
