@@ -795,6 +795,8 @@ static int g_dbg = -1;         // GCBF_TC_DBG experiment switches (read once)
 // number of MMAs accumulated before the chunk sum is promoted to registers with round-to-nearest.  4 k-blocks = 128 K-elements = 24 MMAs
 // per chunk (GCBF_TC_KCH=8 restores the 256-element chunks of round 1; measured on the shipped DubinsCar checkpoint: max|du| 1.0e-5 -> see DESIGN 5)
 static int g_kch = 4;
+static int g_kch_dgrad = 8;     // data-grad products with per-tensor operands keep 256-element chunks: their result is a gradient (parity bar: 2e-2
+                                // of the gradient norm, measured 1e-6), the forward's 1e-5 bar on h / u does not depend on them.  GCBF_TC_KCH_DGRAD
 static int g_emit_direct = 0;   // GCBF_EPI_STORE=direct: emitted companions leave by plain 16-byte stores (experiment)
 static bool g_two_cta = true;
 
@@ -865,8 +867,10 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
   }
   const int tiles_m = ceil_div(Mo, BM * CG), tiles_n = ceil_div(No, BN);   // CG == 2: 256-row pair tiles
   const int kblocks = ceil_div(Kc, BK);
-  // chunks of g_kch k-blocks must not straddle splits (tile-scaled operands: a chunk lies inside one scale tile)
-  const int kps = ceil_div(ceil_div(kblocks, splits), g_kch) * g_kch;
+  const bool tiled_operand = ep.a_sr || ep.a_sc || ep.b_sr || ep.b_sc;
+  const int kch = (!A_MN && B_MN && !tiled_operand) ? g_kch_dgrad : g_kch;
+  // chunks of kch k-blocks must not straddle splits (tile-scaled operands: a chunk lies inside one scale tile)
+  const int kps = ceil_div(ceil_div(kblocks, splits), kch) * kch;
   const int nsplit = ceil_div(kblocks, kps);
   int dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);
@@ -886,7 +890,7 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
   cfg.attrs = attr;
   cfg.numAttrs = (CG == 2) ? 1 : 0;
   GCBF_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_h_kernel<BN, A_MN, B_MN, CG, EMIT>, mah, mal, mbh, mbl, mc, moh, mol, C, ldc, Mo, No, tiles_m, tiles_n, kps,
-                                  kblocks, g_kch, ep));
+                                  kblocks, kch, ep));
   return GCBF_OK;
 }
 
@@ -901,6 +905,9 @@ static int launch(const Operand& A, const Operand& B, float* C, int ldc, int Mo,
     g_two_cta = !(c2 && c2[0] == '0');
     const char* kc = getenv("GCBF_TC_KCH");
     if (kc && atoi(kc) >= 1 && atoi(kc) <= KCH_MAX) g_kch = atoi(kc);
+    const char* kd = getenv("GCBF_TC_KCH_DGRAD");
+    if (kd && atoi(kd) >= 1 && atoi(kd) <= KCH_MAX) g_kch_dgrad = atoi(kd);
+    if (kc && !kd) g_kch_dgrad = g_kch > 4 ? g_kch : g_kch_dgrad;
     const char* es = getenv("GCBF_EPI_STORE");
     g_emit_direct = (es && es[0] == 'd') ? 1 : 0;
   }
