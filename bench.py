@@ -247,6 +247,33 @@ def measure(cfg_name, args, dev, rank, world, dist, with_roofline, sampler=None)
                 scal=scal, gemm=gemm, ms_instr=ms_instr)
 
 
+def rollout_leg(cfg_name, dev, steps=20):
+    """Vectorised data collection (gcbf_b200/algo/rollout.py): all graphs of the config as independent environments,
+    one vector step = u_ref + ONE radius graph + ONE actor forward + masks + dynamics + replay append for all of them.  The
+    reference steps one 16-agent env per ~5 ms of host time."""
+    from gcbf_b200.algo.rollout import VectorRollout
+    sb, env, algo = build_case(cfg_name, dev, 0)
+    B, n = sb.num_graphs, sb.num_agents
+    algo.use_device_replay(capacity=max(64, 4 * B))
+    goals = sb.goals.repeat(B, 1)
+    vr = VectorRollout(env, algo, B, states=sb.states, goals=goals)
+    for _ in range(3):
+        vr.step(prob=0.5)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        vr.step(prob=0.5)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps * 1e3
+    ms = e0.elapsed_time(e1) / steps
+    return {'workload': f'{cfg_name}: {B} environments x {n} agents per vector step (actor forward, env step, masks, replay append)',
+            'ms_per_vector_step': round(ms, 4), 'wall_ms_per_vector_step': round(wall, 4), 'env_steps_per_s': round(B / (wall / 1e3), 1),
+            'agent_steps_per_s': round(B * n / (wall / 1e3), 1), 'host_syncs_per_vector_step': 1}
+
+
 def shape_traffic(dom):
     """DRAM bytes per launch of the dominant launch shape from the committed `ncu --set full` capture of exactly that shape
     (profiles/r02_gemm_h_ncu_full.json: {"launches": [{"product", "M", "N", "K", "dram_read_bytes", "dram_write_bytes"}, ...]});
@@ -350,6 +377,11 @@ def run_own(args):
         'roofline': roofline,
         'loss': round(m['scal'][6], 6),
     }
+    if world == 1 and not args.no_e2e:
+        try:
+            line['rollout'] = [rollout_leg(main_cfg, dev), rollout_leg('C1x256', dev)]
+        except Exception as ex:                                   # the rollout leg is an extra: never lose the bench line over it
+            line['rollout'] = {'error': repr(ex)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(main_cfg, budget_s=25.0)
     print(json.dumps(line), flush=True)

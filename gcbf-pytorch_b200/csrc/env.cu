@@ -92,7 +92,7 @@ __device__ __forceinline__ void u_ref_one(const EnvCfg& c, const float* s, const
 }
 
 __global__ void u_ref_kernel(EnvCfg c, const float* __restrict__ states, int ld, const float* __restrict__ goal,
-                             int ld_goal, const float* __restrict__ K, float* __restrict__ out) {
+                             int ld_goal, int goal_gstride, const float* __restrict__ K, float* __restrict__ out) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= c.num_graphs * c.n) return;
   const int g = a / c.n, il = a % c.n;
@@ -100,14 +100,14 @@ __global__ void u_ref_kernel(EnvCfg c, const float* __restrict__ states, int ld,
   const int ad = c.env == GCBF_ENV_SIMPLE_DRONE ? 3 : 2;
   float s[6], gl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, u[3];   // goal rows narrower than 6 read as zeros
   for (int k = 0; k < sd; ++k) s[k] = states[((size_t)g * c.N + il) * ld + k];
-  for (int k = 0; k < ld_goal && k < 6; ++k) gl[k] = goal[(size_t)il * ld_goal + k];
+  for (int k = 0; k < ld_goal && k < 6; ++k) gl[k] = goal[((size_t)g * goal_gstride + il) * ld_goal + k];   // goal_gstride 0: one goal set for all graphs
   u_ref_one(c, s, gl, K, u);
   for (int k = 0; k < ad; ++k) out[(size_t)a * ad + k] = u[k];
 }
 
 // ---- one dynamics step: x+ = x + dt * f(x, clamp(u + u_ref(x))) ------------------------------------
 __global__ void step_fwd_kernel(EnvCfg c, const float* __restrict__ states, int ld, const float* __restrict__ action,
-                                const float* __restrict__ goal, int ld_goal, const float* __restrict__ K, int freeze,
+                                const float* __restrict__ goal, int ld_goal, int goal_gstride, const float* __restrict__ K, int freeze,
                                 float* __restrict__ next, uint8_t* __restrict__ pass_mask) {
   const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (node >= (int64_t)c.num_graphs * c.N) return;
@@ -121,7 +121,7 @@ __global__ void step_fwd_kernel(EnvCfg c, const float* __restrict__ states, int 
   if (is_agent) {
     const int a = g * c.n + l;
     float gl[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ur[3];
-    for (int k = 0; k < ld_goal && k < 6; ++k) gl[k] = goal[(size_t)l * ld_goal + k];
+    for (int k = 0; k < ld_goal && k < 6; ++k) gl[k] = goal[((size_t)g * goal_gstride + l) * ld_goal + k];
     u_ref_one(c, s, gl, K, ur);
     for (int k = 0; k < ad; ++k) {
       const float raw = __fadd_rn(action[(size_t)a * ad + k], ur[k]);
@@ -260,7 +260,21 @@ extern "C" int gcbf_u_ref(const gcbf_env_cfg* cfg, const float* states, int ld_s
   const int na = c.num_graphs * c.n;
   if (na == 0) return GCBF_OK;
   GCBF_REQUIRE(states && goal && u_ref && (K || c.env == GCBF_ENV_DUBINS_CAR), "gcbf_u_ref: null pointer");
-  u_ref_kernel<<<ceil_div(na, 128), 128, 0, as_stream(stream)>>>(c, states, ld_state, goal, ld_goal, K, u_ref);
+  u_ref_kernel<<<ceil_div(na, 128), 128, 0, as_stream(stream)>>>(c, states, ld_state, goal, ld_goal, 0, K, u_ref);
+  GCBF_LAUNCH_OK();
+  return GCBF_OK;
+}
+
+// the same with ONE GOAL SET PER GRAPH (goal [num_graphs * num_agents, ld_goal]): vectorised rollouts step many independent
+// environments as one batch, each with its own goals
+extern "C" int gcbf_u_ref_multi(const gcbf_env_cfg* cfg, const float* states, int ld_state, const float* goal, int ld_goal,
+                                const float* K, float* u_ref, void* stream) {
+  EnvCfg c;
+  if (int rc = make_cfg(cfg, &c, "gcbf_u_ref_multi")) return rc;
+  const int na = c.num_graphs * c.n;
+  if (na == 0) return GCBF_OK;
+  GCBF_REQUIRE(states && goal && u_ref && (K || c.env == GCBF_ENV_DUBINS_CAR), "gcbf_u_ref_multi: null pointer");
+  u_ref_kernel<<<ceil_div(na, 128), 128, 0, as_stream(stream)>>>(c, states, ld_state, goal, ld_goal, c.n, K, u_ref);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }
@@ -274,7 +288,22 @@ extern "C" int gcbf_step_fwd(const gcbf_env_cfg* cfg, const float* states, int l
   if (nn == 0) return GCBF_OK;
   GCBF_REQUIRE(states && action && goal && states_next && pass_mask && (K || c.env == GCBF_ENV_DUBINS_CAR),
                "gcbf_step_fwd: null pointer");
-  step_fwd_kernel<<<ceil_div(nn, 128), 128, 0, as_stream(stream)>>>(c, states, ld_state, action, goal, ld_goal, K,
+  step_fwd_kernel<<<ceil_div(nn, 128), 128, 0, as_stream(stream)>>>(c, states, ld_state, action, goal, ld_goal, 0, K,
+                                                                   freeze, states_next, pass_mask);
+  GCBF_LAUNCH_OK();
+  return GCBF_OK;
+}
+
+extern "C" int gcbf_step_fwd_multi(const gcbf_env_cfg* cfg, const float* states, int ld_state, const float* action,
+                                   const float* goal, int ld_goal, const float* K, int freeze, float* states_next,
+                                   uint8_t* pass_mask, void* stream) {
+  EnvCfg c;
+  if (int rc = make_cfg(cfg, &c, "gcbf_step_fwd_multi")) return rc;
+  const int64_t nn = (int64_t)c.num_graphs * c.N;
+  if (nn == 0) return GCBF_OK;
+  GCBF_REQUIRE(states && action && goal && states_next && pass_mask && (K || c.env == GCBF_ENV_DUBINS_CAR),
+               "gcbf_step_fwd_multi: null pointer");
+  step_fwd_kernel<<<ceil_div(nn, 128), 128, 0, as_stream(stream)>>>(c, states, ld_state, action, goal, ld_goal, c.n, K,
                                                                    freeze, states_next, pass_mask);
   GCBF_LAUNCH_OK();
   return GCBF_OK;

@@ -110,8 +110,8 @@ static int step_forward(Run& R, const gcbf_step_desc& d, const gcbf_step_batch& 
     CHAIN_CALL(gcbf_masks(&cfg, b.states, b.ld_state, c->safe, c->unsafe, c->coll, main));                                                   // gcbf.py:168, 180
     // graphs_next = env.forward_graph(graphs, actions): retained edges, new edge features  (gcbf.py:193).  A batch of exactly one
     // graph satisfies the reference's single-graph discriminator (dubins_car.py:126): reach-freeze branch
-    CHAIN_CALL(gcbf_step_fwd(&cfg, b.states, b.ld_state, c->actions, d.goal, d.ld_goal, d.lqr_gain, d.env.num_graphs == 1 ? 1 : 0, c->states_next,
-                             c->pass_mask, main));
+    CHAIN_CALL((d.goal_per_graph ? gcbf_step_fwd_multi : gcbf_step_fwd)(&cfg, b.states, b.ld_state, c->actions, d.goal, d.ld_goal, d.lqr_gain,
+                                                                      d.env.num_graphs == 1 ? 1 : 0, c->states_next, c->pass_mask, main));
     CHAIN_CALL(gcbf_edge_attr_fwd(d.env.env, c->states_next, s, b.edge_index, E, c->ea_next, main));
     R.launched(E ? 3 : 2);
     if (two) CHAIN_CUDA(cudaEventRecord(hr->inputs_ready, main));
@@ -121,7 +121,8 @@ static int step_forward(Run& R, const gcbf_step_desc& d, const gcbf_step_batch& 
     if (two) { CHAIN_CUDA(cudaEventRecord(hr->pi2_done, main)); CHAIN_CUDA(cudaStreamWaitEvent(side, hr->inputs_ready, 0)); }
     cudaStream_t rs = two ? side : main;
     // gcbf.py:195-199, batched: every graph is a SINGLE graph there, so the reach-freeze branch applies; then the radius count
-    CHAIN_CALL(gcbf_step_fwd(&cfg, b.states, b.ld_state, c->actions, d.goal, d.ld_goal, d.lqr_gain, 1, c->st_relink, pm_relink, rs));
+    CHAIN_CALL((d.goal_per_graph ? gcbf_step_fwd_multi : gcbf_step_fwd)(&cfg, b.states, b.ld_state, c->actions, d.goal, d.ld_goal, d.lqr_gain, 1,
+                                                                      c->st_relink, pm_relink, rs));
     CHAIN_CALL(gcbf_radius_graph_count(c->st_relink, s, d.pos_dim, d.env.num_graphs, d.env.nodes_per_graph, d.env.num_agents, d.comm_radius,
                                        d.graph_metric, c->rowptr_agents, rs));
     CHAIN_CUDA(cudaMemcpyAsync(hr->e_new_pinned, c->rowptr_agents + M, 4, cudaMemcpyDeviceToHost, rs));

@@ -65,6 +65,8 @@ _SIGS = {
     'gcbf_u_ref': (c_int, [POINTER(EnvCfg), P, c_int, P, c_int, P, P, P]),
     'gcbf_step_fwd': (c_int, [POINTER(EnvCfg), P, c_int, P, P, c_int, P, c_int, P, P, P]),
     'gcbf_step_bwd': (c_int, [POINTER(EnvCfg), P, c_int, P, P, P]),
+    'gcbf_u_ref_multi': (c_int, [POINTER(EnvCfg), P, c_int, P, c_int, P, P, P]),
+    'gcbf_step_fwd_multi': (c_int, [POINTER(EnvCfg), P, c_int, P, P, c_int, P, c_int, P, P, P]),
     'gcbf_masks': (c_int, [POINTER(EnvCfg), P, c_int, P, P, P, P]),
     'gcbf_loss_partials': (c_int, [P, P, P, P, c_int, P, P, c_int64, c_float, c_float, c_float, P, P, P]),
     'gcbf_loss_grads': (c_int, [P, P, P, P, c_int, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float,

@@ -308,6 +308,12 @@ class GCBF(Algorithm):
         B = env._num_graphs_of(graphs)
         cfg = env._cfg(B)
         ctypes.memmove(ctypes.byref(d.env), ctypes.byref(cfg), ctypes.sizeof(_C.EnvCfg))
+        goal_pg = getattr(graphs, 'goal', None) if hasattr(graphs, 'goal') else None       # [B * n, goal_dim]: per-graph goal sets
+        if goal_pg is not None:
+            gpg, ldg = ops._mat(goal_pg.contiguous())
+            d.goal, d.ld_goal, d.goal_per_graph = gpg.data_ptr(), ldg, 1
+        else:
+            d.goal, d.ld_goal, d.goal_per_graph = _keep[0].data_ptr(), ops._mat(_keep[0])[1], 0
         st, ld = ops._mat(graphs.states.detach())
         x, ea, ei = graphs.x.contiguous(), graphs.edge_attr.detach().contiguous(), graphs.edge_index.contiguous()
         uref = graphs.u_ref.contiguous()

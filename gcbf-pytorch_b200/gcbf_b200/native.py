@@ -47,7 +47,7 @@ class StepDesc(ctypes.Structure):
                 ('ld_goal', c_int32), ('state_dim', c_int32), ('pos_dim', c_int32), ('action_dim', c_int32),
                 ('graph_metric', c_int32), ('comm_radius', c_float),
                 ('alpha', c_float), ('eps', c_float), ('coef_unsafe', c_float), ('coef_safe', c_float), ('coef_hdot', c_float),
-                ('coef_action', c_float), ('grad_bucket', P), ('grad_bucket_floats', c_int64)]
+                ('coef_action', c_float), ('grad_bucket', P), ('grad_bucket_floats', c_int64), ('goal_per_graph', c_int32), ('pad_', c_int32)]
 
 
 class StepBatch(ctypes.Structure):

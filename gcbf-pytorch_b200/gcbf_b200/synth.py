@@ -89,7 +89,9 @@ CONFIGS = {
 }
 # graphs one GPU owns (bench.py is weak scaling: every rank gets this many).  C4 / C5 are defined over 8 GPUs in
 # BASELINE.json (16 replicas -> 2 per GPU, 8 dense graphs -> 1 per GPU); C1..C3 are single-GPU batches.
-GRAPHS_PER_GPU = {'C1': 1, 'C2': 32, 'C3': 64, 'C4': 2, 'C5': 1}
+GRAPHS_PER_GPU = {'C1': 1, 'C2': 32, 'C3': 64, 'C4': 2, 'C5': 1, 'C1x256': 256}
+# (C1x256: 256 copies of the reference's own training scale -- 16 agents in a 4 x 4 area -- as vectorised rollout environments)
+CONFIGS['C1x256'] = dict(env='SimpleCar', num_agents=16, num_obs=0, num_graphs=256, area_size=4.0, seed=1011)
 
 
 def seeded_algo(env_name, n, device, init_seed=0, env_params=None, hyperparams='table'):

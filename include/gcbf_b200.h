@@ -234,6 +234,13 @@ int gcbf_step_fwd(const gcbf_env_cfg* cfg, const float* states, int ld_state, co
                   uint8_t* pass_mask, void* stream);
 int gcbf_step_bwd(const gcbf_env_cfg* cfg, const float* d_states_next, int ld_state,
                   const uint8_t* pass_mask, float* d_action, void* stream);
+/* the same two with ONE GOAL SET PER GRAPH, goal [num_graphs * num_agents, ld_goal]: many independent environments (each with
+ * its own goals) stepped as one batch -- the vectorised rollout of gcbf/trainer/trainer.py:60-70 + gcbf/algo/gcbf.py:128-139 */
+int gcbf_u_ref_multi(const gcbf_env_cfg* cfg, const float* states, int ld_state, const float* goal, int ld_goal,
+                     const float* K, float* u_ref, void* stream);
+int gcbf_step_fwd_multi(const gcbf_env_cfg* cfg, const float* states, int ld_state, const float* action,
+                        const float* goal, int ld_goal, const float* K, int freeze, float* states_next,
+                        uint8_t* pass_mask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * K6  safe / unsafe masks and the CBF losses.
@@ -370,12 +377,13 @@ int gcbf_mlp_backward(const gcbf_linear_desc* layers, int n_layers, const gcbf_m
 typedef struct gcbf_step_desc {
   gcbf_net_desc cbf, actor;
   gcbf_env_cfg env;
-  const float* goal; const float* lqr_gain;     /* goal [num_agents, ld_goal]; LQR gain or NULL (DubinsCar) */
+  const float* goal; const float* lqr_gain;     /* goal [num_agents, ld_goal] (or [num_graphs * num_agents, ld_goal] with goal_per_graph); LQR gain or NULL (DubinsCar) */
   int32_t ld_goal, state_dim, pos_dim, action_dim;
   int32_t graph_metric;                          /* K1 metric: 0 SimpleCar, 1 DubinsCar / SimpleDrone */
   float comm_radius;
   float alpha, eps, coef_unsafe, coef_safe, coef_hdot, coef_action;
   float* grad_bucket; int64_t grad_bucket_floats;   /* zeroed by gcbf_step_backward before the gradients accumulate (NULL: caller zeroes) */
+  int32_t goal_per_graph; int32_t pad_;             /* != 0: every graph of the batch has its own goal set (batches collected by vectorised rollouts) */
 } gcbf_step_desc;
 
 typedef struct gcbf_step_batch {
