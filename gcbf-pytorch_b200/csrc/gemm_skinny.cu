@@ -94,10 +94,13 @@ __device__ __forceinline__ uint32_t skinny_scale_bits(uint32_t amax_bits) {     
   return (uint32_t)se << 23;
 }
 
-__global__ void __launch_bounds__(256) skinny_fwd_emit_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
-                                                              const float* __restrict__ bias, const float* __restrict__ alpha_p,
-                                                              __half* __restrict__ Yh, int ld_h, uint32_t* __restrict__ tile_amax,
-                                                              int amax_stride, int M, int N, int K, int act) {
+__global__ void __launch_bounds__(256, 1) skinny_fwd_emit_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+                                                                 const float* __restrict__ bias, const float* __restrict__ alpha_p,
+                                                                 __half* __restrict__ Yh, int ld_h, uint32_t* __restrict__ tile_amax,
+                                                                 int amax_stride, int M, int N, int K, int act) {
+  // one block = one 128-row x 256-column tile; thread = 4 consecutive columns x 32 rows, all 128 results kept in registers between
+  // the maximum and the conversion (the first version recomputed the tile for the second pass: 2 x 16 FMA per output made the
+  // kernel FP32-bound at 23 % of the HBM rate)
   __shared__ __align__(16) float xs[128][SK];
   __shared__ uint32_t wmax[8];
   const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;              // 64 column groups of 4 x 4 row groups of 32
@@ -116,63 +119,64 @@ __global__ void __launch_bounds__(256) skinny_fwd_emit_kernel(const float* __res
   }
   __syncthreads();
   const int rows = min(128, M - m0);
-  float s = 1.f;
-  const size_t plane = (size_t)M * ld_h;
-  const bool vec = (n0 + 4 <= N);
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    float ymax = 0.f;
-    for (int r = rg * 32; r < min(rows, rg * 32 + 32); ++r) {
-      const float4* xr = reinterpret_cast<const float4*>(xs[r]);
-      float y[4] = {0.f, 0.f, 0.f, 0.f};
+  float y[32][4];
+  float ymax = 0.f;
 #pragma unroll
-      for (int q = 0; q < SK / 4; ++q) {
-        const float4 v = xr[q];
+  for (int i = 0; i < 32; ++i) {
+    const float4* xr = reinterpret_cast<const float4*>(xs[rg * 32 + i]);
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          y[c] = fmaf(v.x, w[c][4 * q], y[c]); y[c] = fmaf(v.y, w[c][4 * q + 1], y[c]);
-          y[c] = fmaf(v.z, w[c][4 * q + 2], y[c]); y[c] = fmaf(v.w, w[c][4 * q + 3], y[c]);
-        }
-      }
+    for (int q = 0; q < SK / 4; ++q) {
+      const float4 v = xr[q];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        y[c] += b[c];
-        if (act == GCBF_ACT_RELU) y[c] = fmaxf(y[c], 0.f);
-        else if (act == GCBF_ACT_TANH) y[c] = tanhf(y[c]);
-        if (n0 + c >= N) y[c] = 0.f;
-      }
-      if (pass == 0) {
-        ymax = fmaxf(fmaxf(ymax, fmaxf(fabsf(y[0]), fabsf(y[1]))), fmaxf(fabsf(y[2]), fabsf(y[3])));
-      } else {
-        const float y0 = y[0] * s, y1 = y[1] * s, y2 = y[2] * s, y3 = y[3] * s;
-        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
-        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-        const __half2 l01 = __floats2half2_rn(__fsub_rn(y0, f01.x), __fsub_rn(y1, f01.y));
-        const __half2 l23 = __floats2half2_rn(__fsub_rn(y2, f23.x), __fsub_rn(y3, f23.y));
-        __half* d = Yh + (size_t)(m0 + r) * ld_h + n0;
-        if (vec) {
-          uint2 hi, lo;
-          hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-          lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
-          *reinterpret_cast<uint2*>(d) = hi;
-          *reinterpret_cast<uint2*>(d + plane) = lo;
-        } else {
-          const __half hs[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
-          const __half ls[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
-          for (int c = 0; c < 4; ++c)
-            if (n0 + c < N) { d[c] = hs[c]; d[plane + c] = ls[c]; }
-        }
+        t[c] = fmaf(v.x, w[c][4 * q], t[c]); t[c] = fmaf(v.y, w[c][4 * q + 1], t[c]);
+        t[c] = fmaf(v.z, w[c][4 * q + 2], t[c]); t[c] = fmaf(v.w, w[c][4 * q + 3], t[c]);
       }
     }
-    if (pass == 0) {
-      const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(ymax));   // non-negative floats order like uints
-      if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
-      __syncthreads();
-      uint32_t t = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t = max(t, wmax[i]);
-      s = __uint_as_float(skinny_scale_bits(t));
-      if (threadIdx.x == 0) tile_amax[(size_t)blockIdx.y * amax_stride + blockIdx.x] = t;
+    for (int c = 0; c < 4; ++c) {
+      t[c] += b[c];
+      if (act == GCBF_ACT_RELU) t[c] = fmaxf(t[c], 0.f);
+      else if (act == GCBF_ACT_TANH) t[c] = tanhf(t[c]);
+      if (n0 + c >= N || rg * 32 + i >= rows) t[c] = 0.f;
+      y[i][c] = t[c];
+      ymax = fmaxf(ymax, fabsf(t[c]));
+    }
+  }
+  {
+    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(ymax));   // non-negative floats order like uints
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  }
+  __syncthreads();
+  uint32_t tm = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tm = max(tm, wmax[i]);
+  const float s = __uint_as_float(skinny_scale_bits(tm));
+  if (threadIdx.x == 0) tile_amax[(size_t)blockIdx.y * amax_stride + blockIdx.x] = tm;
+  const size_t plane = (size_t)M * ld_h;
+  const bool vec = (n0 + 4 <= N);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int r = rg * 32 + i;
+    if (r >= rows) break;
+    const float y0 = y[i][0] * s, y1 = y[i][1] * s, y2 = y[i][2] * s, y3 = y[i][3] * s;
+    const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(__fsub_rn(y0, f01.x), __fsub_rn(y1, f01.y));
+    const __half2 l23 = __floats2half2_rn(__fsub_rn(y2, f23.x), __fsub_rn(y3, f23.y));
+    __half* d = Yh + (size_t)(m0 + r) * ld_h + n0;
+    if (vec) {
+      uint2 hi, lo;
+      hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+      lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(d) = hi;
+      *reinterpret_cast<uint2*>(d + plane) = lo;
+    } else {
+      const __half hs[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
+      const __half ls[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
+      for (int c = 0; c < 4; ++c)
+        if (n0 + c < N) { d[c] = hs[c]; d[plane + c] = ls[c]; }
     }
   }
 }
