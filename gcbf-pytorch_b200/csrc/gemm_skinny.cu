@@ -98,13 +98,14 @@ __global__ void __launch_bounds__(256, 1) skinny_fwd_emit_kernel(const float* __
                                                                  const float* __restrict__ bias, const float* __restrict__ alpha_p,
                                                                  __half* __restrict__ Yh, int ld_h, uint32_t* __restrict__ tile_amax,
                                                                  int amax_stride, int M, int N, int K, int act) {
-  // one block = one 128-row x 256-column tile; thread = 4 consecutive columns x 32 rows, all 128 results kept in registers between
-  // the maximum and the conversion (the first version recomputed the tile for the second pass: 2 x 16 FMA per output made the
-  // kernel FP32-bound at 23 % of the HBM rate)
+  // A block owns one 256-column tile and walks down the 128-row tiles (persistent: ~one block per SM): its 4 x 16 weights per thread
+  // are loaded ONCE, the next row tile's inputs are prefetched into registers while the current one is computed.  thread = 4
+  // consecutive columns x 32 rows, all 128 results stay in registers between the tile maximum and the conversion.  (v1 recomputed the
+  // tile for the conversion pass and re-loaded the weights per tile: 1.1 ms per 206 k-row launch = 23 % of the HBM rate.)
   __shared__ __align__(16) float xs[128][SK];
-  __shared__ uint32_t wmax[8];
+  __shared__ uint32_t wmax[2][8];
   const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;              // 64 column groups of 4 x 4 row groups of 32
-  const int n0 = blockIdx.x * 256 + cg * 4, m0 = blockIdx.y * 128;
+  const int n0 = blockIdx.x * 256 + cg * 4;
   const float alpha = alpha_p ? __ldg(alpha_p) : 1.f;
   float w[4][SK], b[4];
 #pragma unroll
@@ -113,70 +114,86 @@ __global__ void __launch_bounds__(256, 1) skinny_fwd_emit_kernel(const float* __
     for (int k = 0; k < SK; ++k) w[c][k] = (n0 + c < N && k < K) ? __ldg(W + (size_t)(n0 + c) * ldw + k) * alpha : 0.f;
     b[c] = (n0 + c < N && bias) ? __ldg(bias + n0 + c) : 0.f;
   }
-  for (int i = threadIdx.x; i < 128 * SK; i += 256) {
-    const int r = i / SK, k = i % SK;
-    xs[r][k] = (m0 + r < M && k < K) ? X[(size_t)(m0 + r) * ldx + k] : 0.f;
-  }
-  __syncthreads();
-  const int rows = min(128, M - m0);
-  float y[32][4];
-  float ymax = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float4* xr = reinterpret_cast<const float4*>(xs[rg * 32 + i]);
-    float t[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < SK / 4; ++q) {
-      const float4 v = xr[q];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        t[c] = fmaf(v.x, w[c][4 * q], t[c]); t[c] = fmaf(v.y, w[c][4 * q + 1], t[c]);
-        t[c] = fmaf(v.z, w[c][4 * q + 2], t[c]); t[c] = fmaf(v.w, w[c][4 * q + 3], t[c]);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      t[c] += b[c];
-      if (act == GCBF_ACT_RELU) t[c] = fmaxf(t[c], 0.f);
-      else if (act == GCBF_ACT_TANH) t[c] = tanhf(t[c]);
-      if (n0 + c >= N || rg * 32 + i >= rows) t[c] = 0.f;
-      y[i][c] = t[c];
-      ymax = fmaxf(ymax, fabsf(t[c]));
-    }
-  }
-  {
-    const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(ymax));   // non-negative floats order like uints
-    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
-  }
-  __syncthreads();
-  uint32_t tm = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tm = max(tm, wmax[i]);
-  const float s = __uint_as_float(skinny_scale_bits(tm));
-  if (threadIdx.x == 0) tile_amax[(size_t)blockIdx.y * amax_stride + blockIdx.x] = tm;
+  const int row_tiles = (M + 127) / 128;
   const size_t plane = (size_t)M * ld_h;
   const bool vec = (n0 + 4 <= N);
+  float pre[8];                                                       // 128 x 16 staged inputs / 256 threads
+  auto prefetch = [&](int rt) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int r = rg * 32 + i;
-    if (r >= rows) break;
-    const float y0 = y[i][0] * s, y1 = y[i][1] * s, y2 = y[i][2] * s, y3 = y[i][3] * s;
-    const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
-    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn(__fsub_rn(y0, f01.x), __fsub_rn(y1, f01.y));
-    const __half2 l23 = __floats2half2_rn(__fsub_rn(y2, f23.x), __fsub_rn(y3, f23.y));
-    __half* d = Yh + (size_t)(m0 + r) * ld_h + n0;
-    if (vec) {
-      uint2 hi, lo;
-      hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-      lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
-      *reinterpret_cast<uint2*>(d) = hi;
-      *reinterpret_cast<uint2*>(d + plane) = lo;
-    } else {
-      const __half hs[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
-      const __half ls[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
-      for (int c = 0; c < 4; ++c)
-        if (n0 + c < N) { d[c] = hs[c]; d[plane + c] = ls[c]; }
+    for (int j = 0; j < 8; ++j) {
+      const int i = threadIdx.x + 256 * j, r = i / SK, k = i % SK;
+      const int row = rt * 128 + r;
+      pre[j] = (rt < row_tiles && row < M && k < K) ? __ldg(X + (size_t)row * ldx + k) : 0.f;
+    }
+  };
+  prefetch(blockIdx.y);
+  int par = 0;
+  for (int rt = blockIdx.y; rt < row_tiles; rt += gridDim.y, par ^= 1) {
+    const int m0 = rt * 128;
+    __syncthreads();                                                  // the previous tile's reads of xs are done
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int i = threadIdx.x + 256 * j; xs[i / SK][i % SK] = pre[j]; }
+    __syncthreads();
+    prefetch(rt + gridDim.y);                                         // in flight during the compute below
+    const int rows = min(128, M - m0);
+    float y[32][4];
+    float ymax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float4* xr = reinterpret_cast<const float4*>(xs[rg * 32 + i]);
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < SK / 4; ++q) {
+        const float4 v = xr[q];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          t[c] = fmaf(v.x, w[c][4 * q], t[c]); t[c] = fmaf(v.y, w[c][4 * q + 1], t[c]);
+          t[c] = fmaf(v.z, w[c][4 * q + 2], t[c]); t[c] = fmaf(v.w, w[c][4 * q + 3], t[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        t[c] += b[c];
+        if (act == GCBF_ACT_RELU) t[c] = fmaxf(t[c], 0.f);
+        else if (act == GCBF_ACT_TANH) t[c] = tanhf(t[c]);
+        if (n0 + c >= N || rg * 32 + i >= rows) t[c] = 0.f;
+        y[i][c] = t[c];
+        ymax = fmaxf(ymax, fabsf(t[c]));
+      }
+    }
+    {
+      const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(ymax));   // non-negative floats order like uints
+      if ((threadIdx.x & 31) == 0) wmax[par][threadIdx.x >> 5] = m;
+    }
+    __syncthreads();
+    uint32_t tm = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tm = max(tm, wmax[par][i]);
+    const float s = __uint_as_float(skinny_scale_bits(tm));
+    if (threadIdx.x == 0) tile_amax[(size_t)rt * amax_stride + blockIdx.x] = tm;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int r = rg * 32 + i;
+      if (r < rows) {
+        const float y0 = y[i][0] * s, y1 = y[i][1] * s, y2 = y[i][2] * s, y3 = y[i][3] * s;
+        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(__fsub_rn(y0, f01.x), __fsub_rn(y1, f01.y));
+        const __half2 l23 = __floats2half2_rn(__fsub_rn(y2, f23.x), __fsub_rn(y3, f23.y));
+        __half* d = Yh + (size_t)(m0 + r) * ld_h + n0;
+        if (vec) {
+          uint2 hi, lo;
+          hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+          lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(d) = hi;
+          *reinterpret_cast<uint2*>(d + plane) = lo;
+        } else {
+          const __half hs[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
+          const __half ls[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
+          for (int c = 0; c < 4; ++c)
+            if (n0 + c < N) { d[c] = hs[c]; d[plane + c] = ls[c]; }
+        }
+      }
     }
   }
 }
@@ -322,8 +339,9 @@ int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const fl
 
 int launch_skinny_fwd_emit(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, __half* Yh, int ld_h,
                            uint32_t* tile_amax, int amax_stride, int M, int N, int K, int act, cudaStream_t st) {
-  skinny_fwd_emit_kernel<<<dim3(ceil_div(N, 256), ceil_div(M, 128)), 256, 0, st>>>(X, ldx, W, ldw, bias, inv_sigma, Yh, ld_h, tile_amax, amax_stride,
-                                                                                M, N, K, act);
+  const int col_tiles = ceil_div(N, 256), row_tiles = ceil_div(M, 128);
+  const int gy = max(1, min(row_tiles, kNumSMs / col_tiles));          // persistent: about one 256-thread block per SM
+  skinny_fwd_emit_kernel<<<dim3(col_tiles, gy), 256, 0, st>>>(X, ldx, W, ldw, bias, inv_sigma, Yh, ld_h, tile_amax, amax_stride, M, N, K, act);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }
