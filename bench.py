@@ -254,7 +254,7 @@ def rollout_leg(cfg_name, dev, steps=20):
     from gcbf_b200.algo.rollout import VectorRollout
     sb, env, algo = build_case(cfg_name, dev, 0)
     B, n = sb.num_graphs, sb.num_agents
-    algo.use_device_replay(capacity=max(64, 4 * B))
+    algo.use_device_replay(capacity=(steps + 4) * B)      # ring sized up front: no regrowth inside the timed loop
     goals = sb.goals.repeat(B, 1)
     vr = VectorRollout(env, algo, B, states=sb.states, goals=goals)
     for _ in range(3):
