@@ -91,3 +91,40 @@ def test_rollout_feeds_the_replay_ring_and_the_train_step_uses_per_graph_goals()
     shared = Data(**{k: batch[k] for k in batch.keys() if k != 'goal'})
     res_sh = algo.train_step(shared, apply_optim=False)
     assert (res_sh['h_next'] - hn_pg).abs().max().item() > 0
+
+
+@pytest.mark.parametrize('env_name,n,obs,area', [('DubinsCar', 12, 4, 2.0), ('SimpleCar', 14, 0, 1.5), ('SimpleDrone', 6, 6, 1.0)])
+def test_device_collate_against_the_oracle(env_name, n, obs, area):
+    """`Batch.from_data_list` (gcbf/algo/gcbf.py:159: block-diagonal collation with edge_index offsets) as the device ring does it -- two
+    gathers + ONE batched radius graph + edge features -- against the ORACLE's collation of the same graphs (per-graph radius graph +
+    offsets, edge features, node types): edge_index bit-exact, everything else equal."""
+    from gcbf_b200.algo.device_buffer import DeviceReplay, collate
+    env, algo = seeded_algo(env_name, n, DEV, 0, {'num_obs': obs, 'area_size': area})
+    ring = DeviceReplay(DEV, capacity=8)
+    stored = []
+    goal = None
+    for k in range(11):                                                      # wraps the ring's initial capacity
+        sbk = synth.make_states(env_name, n, obs, 1, area, 700 + k)
+        if goal is None:
+            goal = sbk.goals
+            env.set_goal(goal)
+            if env_name == 'DubinsCar':
+                env._obs = sbk.obs.to(DEV)
+        g = env.graph_from_states(sbk.states.to(DEV))
+        ring.append(g, is_safe=(k % 2 == 0))
+        stored.append(sbk)
+    idx = [9, 2, 3, 10, 0]
+    batch = collate(env, [(ring, idx)])
+    N = stored[0].nodes_per_graph
+    states = torch.cat([stored[i].states for i in idx], dim=0)
+    ei = O.batch_radius_graph(env_name, states, len(idx), N, n)
+    assert torch.equal(batch.edge_index.cpu(), ei)
+    assert torch.equal(batch.states.cpu(), states)
+    assert (batch.edge_attr.cpu() - O.edge_attr(env_name, states, ei)).abs().max().item() <= 1e-6
+    x, am = O.make_graph_inputs(env_name, states, len(idx), n, stored[0].num_obs)
+    assert torch.equal(batch.x.cpu(), x)
+    if am is not None:
+        assert torch.equal(batch.agent_mask.cpu(), am)
+    K = O.lqr_gain(env_name) if env_name != 'DubinsCar' else None
+    ur = O.u_ref(env_name, states if am is None else states[am], goal, K)
+    assert (batch.u_ref.cpu() - ur).abs().max().item() <= 1e-5
