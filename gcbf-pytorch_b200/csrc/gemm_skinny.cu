@@ -275,6 +275,59 @@ __global__ void __launch_bounds__(256) skinny_dgrad_kernel(const float* __restri
   }
 }
 
+// data-grad with the WHOLE W^T resident in shared memory (N <= 3072: 16 x (N + 4) floats <= 197 KB): persistent blocks stage it once
+// and stream their rows -- the chunked kernel above re-stages 128 KB of W per 32 rows, half as much again as the dZ bytes it reads
+constexpr int SKD_RPW = 8;
+__global__ void __launch_bounds__(256, 1) skinny_dgrad_full_kernel(const float* __restrict__ dZ, int lddz, const float* __restrict__ W, int ldw,
+                                                                   const float* __restrict__ alpha_p, const float* __restrict__ relu_src,
+                                                                   int ld_relu, float* __restrict__ dX, int lddx, int M, int N, int K,
+                                                                   int accumulate) {
+  extern __shared__ __align__(16) float wt_full[];                 // [SK][N + 4]
+  const int pitch = N + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < SK * N; i += 256) {
+    const int n = i / SK, k = i % SK;
+    wt_full[k * pitch + n] = (k < K) ? __ldg(W + (size_t)n * ldw + k) : 0.f;
+  }
+  __syncthreads();
+  const float alpha = alpha_p ? __ldg(alpha_p) : 1.f;
+  for (int mb = blockIdx.x * (8 * SKD_RPW); mb < M; mb += gridDim.x * (8 * SKD_RPW)) {
+    const int m0 = mb + warp * SKD_RPW;
+    float acc[SKD_RPW][SK];
+#pragma unroll
+    for (int r = 0; r < SKD_RPW; ++r)
+#pragma unroll
+      for (int k = 0; k < SK; ++k) acc[r][k] = 0.f;
+    for (int n = lane * 4; n < N; n += 128) {
+      float4 z[SKD_RPW];
+#pragma unroll
+      for (int r = 0; r < SKD_RPW; ++r)
+        z[r] = (m0 + r < M) ? __ldg(reinterpret_cast<const float4*>(dZ + (size_t)(m0 + r) * lddz + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < SK; ++k) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&wt_full[k * pitch + n]);
+#pragma unroll
+        for (int r = 0; r < SKD_RPW; ++r)
+          acc[r][k] = fmaf(z[r].w, w4.w, fmaf(z[r].z, w4.z, fmaf(z[r].y, w4.y, fmaf(z[r].x, w4.x, acc[r][k]))));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SKD_RPW; ++r) {
+      const int m = m0 + r;
+#pragma unroll
+      for (int k = 0; k < SK; ++k) {
+        const float sum = warp_sum(acc[r][k]);
+        if (lane == k && k < K && m < M) {
+          float v = alpha * sum;
+          if (relu_src && !(relu_src[(size_t)m * ld_relu + k] > 0.f)) v = 0.f;
+          float* dst = dX + (size_t)m * lddx + k;
+          *dst = accumulate ? *dst + v : v;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restrict__ dZ, int lddz, const float* __restrict__ X,
                                                            int ldx, const float* __restrict__ alpha_p, float* __restrict__ dW,
                                                            int lddw, float* __restrict__ db, int M, int N, int K,
@@ -408,9 +461,20 @@ int launch_skinny_fwd_emit(const float* X, int ldx, const float* W, int ldw, con
 
 int launch_skinny_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src,
                         int ld_relu, float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st) {
+  const int vec_ok = ((lddz & 3) == 0 && (reinterpret_cast<uintptr_t>(dZ) & 15) == 0) ? 1 : 0;
+  if (vec_ok && (N & 3) == 0 && N <= 3072 && M >= 4096) {
+    const size_t smem = (size_t)SK * (N + 4) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      GCBF_CUDA_OK(cudaFuncSetAttribute(skinny_dgrad_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK * (3072 + 4) * (int)sizeof(float)));
+      attr_set = true;
+    }
+    skinny_dgrad_full_kernel<<<kNumSMs, 256, smem, st>>>(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate);
+    GCBF_LAUNCH_OK();
+    return GCBF_OK;
+  }
   const int rpb = 32;                       // 8 warps x 4 rows: W^T is staged once per block
   const int blocks = ceil_div(M, rpb);
-  const int vec_ok = ((lddz & 3) == 0 && (reinterpret_cast<uintptr_t>(dZ) & 15) == 0) ? 1 : 0;
   skinny_dgrad_kernel<<<blocks, 256, 0, st>>>(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, rpb, vec_ok);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
