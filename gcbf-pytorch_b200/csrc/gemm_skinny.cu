@@ -94,34 +94,35 @@ __device__ __forceinline__ uint32_t skinny_scale_bits(uint32_t amax_bits) {     
   return (uint32_t)se << 23;
 }
 
-__global__ void __launch_bounds__(256, 1) skinny_fwd_emit_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
+__global__ void __launch_bounds__(512, 1) skinny_fwd_emit_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
                                                                  const float* __restrict__ bias, const float* __restrict__ alpha_p,
                                                                  __half* __restrict__ Yh, int ld_h, uint32_t* __restrict__ tile_amax,
                                                                  int amax_stride, int M, int N, int K, int act) {
-  // A block owns one 256-column tile and walks down the 128-row tiles (persistent: ~one block per SM): its 4 x 16 weights per thread
-  // are loaded ONCE, the next row tile's inputs are prefetched into registers while the current one is computed.  thread = 4
-  // consecutive columns x 32 rows, all 128 results stay in registers between the tile maximum and the conversion.  (v1 recomputed the
-  // tile for the conversion pass and re-loaded the weights per tile: 1.1 ms per 206 k-row launch = 23 % of the HBM rate.)
+  // A block (512 threads = 16 warps, one per SM) owns one 256-column tile and walks down the 128-row tiles: its 2 x 16 weights per
+  // thread are loaded ONCE, the next row tile's inputs are prefetched into registers while the current one is computed.  thread = 2
+  // adjacent columns x 32 rows; the 64 results stay in registers between the tile maximum and the conversion.  (v1 recomputed the
+  // tile for the conversion pass and re-loaded the weights per tile: 1.08 ms per 206 k-row launch; v2 kept 4 x 32 results per thread in
+  // 231 registers -> 8 warps per SM: 0.87 ms.)
   __shared__ __align__(16) float xs[128][SK];
-  __shared__ uint32_t wmax[2][8];
-  const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;              // 64 column groups of 4 x 4 row groups of 32
-  const int n0 = blockIdx.x * 256 + cg * 4;
+  __shared__ uint32_t wmax[2][16];
+  const int cg = threadIdx.x & 127, rg = threadIdx.x >> 7;            // 128 column pairs x 4 row groups of 32
+  const int n0 = blockIdx.x * 256 + cg * 2;
   const float alpha = alpha_p ? __ldg(alpha_p) : 1.f;
-  float w[4][SK], b[4];
+  float w[2][SK], b[2];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
 #pragma unroll
     for (int k = 0; k < SK; ++k) w[c][k] = (n0 + c < N && k < K) ? __ldg(W + (size_t)(n0 + c) * ldw + k) * alpha : 0.f;
     b[c] = (n0 + c < N && bias) ? __ldg(bias + n0 + c) : 0.f;
   }
   const int row_tiles = (M + 127) / 128;
   const size_t plane = (size_t)M * ld_h;
-  const bool vec = (n0 + 4 <= N);
-  float pre[8];                                                       // 128 x 16 staged inputs / 256 threads
+  const bool vec = (n0 + 2 <= N);
+  float pre[4];                                                       // 128 x 16 staged inputs / 512 threads
   auto prefetch = [&](int rt) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = threadIdx.x + 256 * j, r = i / SK, k = i % SK;
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + 512 * j, r = i / SK, k = i % SK;
       const int row = rt * 128 + r;
       pre[j] = (rt < row_tiles && row < M && k < K) ? __ldg(X + (size_t)row * ldx + k) : 0.f;
     }
@@ -132,34 +133,30 @@ __global__ void __launch_bounds__(256, 1) skinny_fwd_emit_kernel(const float* __
     const int m0 = rt * 128;
     __syncthreads();                                                  // the previous tile's reads of xs are done
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int i = threadIdx.x + 256 * j; xs[i / SK][i % SK] = pre[j]; }
+    for (int j = 0; j < 4; ++j) { const int i = threadIdx.x + 512 * j; xs[i / SK][i % SK] = pre[j]; }
     __syncthreads();
     prefetch(rt + gridDim.y);                                         // in flight during the compute below
     const int rows = min(128, M - m0);
-    float y[32][4];
+    float y[32][2];
     float ymax = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const float4* xr = reinterpret_cast<const float4*>(xs[rg * 32 + i]);
-      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      float t0 = 0.f, t1 = 0.f;
 #pragma unroll
       for (int q = 0; q < SK / 4; ++q) {
         const float4 v = xr[q];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          t[c] = fmaf(v.x, w[c][4 * q], t[c]); t[c] = fmaf(v.y, w[c][4 * q + 1], t[c]);
-          t[c] = fmaf(v.z, w[c][4 * q + 2], t[c]); t[c] = fmaf(v.w, w[c][4 * q + 3], t[c]);
-        }
+        t0 = fmaf(v.x, w[0][4 * q], t0); t0 = fmaf(v.y, w[0][4 * q + 1], t0); t0 = fmaf(v.z, w[0][4 * q + 2], t0); t0 = fmaf(v.w, w[0][4 * q + 3], t0);
+        t1 = fmaf(v.x, w[1][4 * q], t1); t1 = fmaf(v.y, w[1][4 * q + 1], t1); t1 = fmaf(v.z, w[1][4 * q + 2], t1); t1 = fmaf(v.w, w[1][4 * q + 3], t1);
       }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        t[c] += b[c];
-        if (act == GCBF_ACT_RELU) t[c] = fmaxf(t[c], 0.f);
-        else if (act == GCBF_ACT_TANH) t[c] = tanhf(t[c]);
-        if (n0 + c >= N || rg * 32 + i >= rows) t[c] = 0.f;
-        y[i][c] = t[c];
-        ymax = fmaxf(ymax, fabsf(t[c]));
-      }
+      t0 += b[0]; t1 += b[1];
+      if (act == GCBF_ACT_RELU) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+      else if (act == GCBF_ACT_TANH) { t0 = tanhf(t0); t1 = tanhf(t1); }
+      const bool row_in = rg * 32 + i < rows;
+      if (!row_in || n0 >= N) t0 = 0.f;
+      if (!row_in || n0 + 1 >= N) t1 = 0.f;
+      y[i][0] = t0; y[i][1] = t1;
+      ymax = fmaxf(ymax, fmaxf(fabsf(t0), fabsf(t1)));
     }
     {
       const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(ymax));   // non-negative floats order like uints
@@ -168,30 +165,24 @@ __global__ void __launch_bounds__(256, 1) skinny_fwd_emit_kernel(const float* __
     __syncthreads();
     uint32_t tm = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tm = max(tm, wmax[par][i]);
+    for (int i = 0; i < 16; ++i) tm = max(tm, wmax[par][i]);
     const float s = __uint_as_float(skinny_scale_bits(tm));
     if (threadIdx.x == 0) tile_amax[(size_t)rt * amax_stride + blockIdx.x] = tm;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const int r = rg * 32 + i;
       if (r < rows) {
-        const float y0 = y[i][0] * s, y1 = y[i][1] * s, y2 = y[i][2] * s, y3 = y[i][3] * s;
-        const __half2 h01 = __floats2half2_rn(y0, y1), h23 = __floats2half2_rn(y2, y3);
-        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-        const __half2 l01 = __floats2half2_rn(__fsub_rn(y0, f01.x), __fsub_rn(y1, f01.y));
-        const __half2 l23 = __floats2half2_rn(__fsub_rn(y2, f23.x), __fsub_rn(y3, f23.y));
+        const float y0 = y[i][0] * s, y1 = y[i][1] * s;
+        const __half2 h = __floats2half2_rn(y0, y1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(__fsub_rn(y0, hf.x), __fsub_rn(y1, hf.y));
         __half* d = Yh + (size_t)(m0 + r) * ld_h + n0;
         if (vec) {
-          uint2 hi, lo;
-          hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-          lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
-          *reinterpret_cast<uint2*>(d) = hi;
-          *reinterpret_cast<uint2*>(d + plane) = lo;
-        } else {
-          const __half hs[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
-          const __half ls[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
-          for (int c = 0; c < 4; ++c)
-            if (n0 + c < N) { d[c] = hs[c]; d[plane + c] = ls[c]; }
+          *reinterpret_cast<__half2*>(d) = h;
+          *reinterpret_cast<__half2*>(d + plane) = l;
+        } else if (n0 < N) {
+          d[0] = __low2half(h);
+          d[plane] = __low2half(l);
         }
       }
     }
@@ -375,66 +366,6 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const float* __restri
   }
 }
 
-// the same for 16-byte aligned dZ rows: thread = 4 adjacent columns (one 16-byte load per row instead of four 4-byte loads,
-// the staged X row is read once per 4 columns: 1 shared load per 16 FMAs instead of per 4)
-__global__ void __launch_bounds__(256) skinny_wgrad4_kernel(const float* __restrict__ dZ, int lddz, const float* __restrict__ X,
-                                                            int ldx, const float* __restrict__ alpha_p, float* __restrict__ dW,
-                                                            int lddw, float* __restrict__ db, int M, int N, int K,
-                                                            int rows_per_block) {
-  __shared__ __align__(16) float xs[SK_ROWS][SK];
-  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
-  float acc[4][SK];
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-#pragma unroll
-    for (int k = 0; k < SK; ++k) acc[c][k] = 0.f;
-  float accb[4] = {0.f, 0.f, 0.f, 0.f};
-  const int m_begin = blockIdx.y * rows_per_block, m_end = min(M, m_begin + rows_per_block);
-  for (int m0 = m_begin; m0 < m_end; m0 += SK_ROWS) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < SK_ROWS * SK; i += 256) {
-      const int r = i / SK, k = i % SK;
-      xs[r][k] = (m0 + r < m_end && k < K) ? X[(size_t)(m0 + r) * ldx + k] : 0.f;
-    }
-    __syncthreads();
-    if (n < N) {
-      const int rows = min(SK_ROWS, m_end - m0);
-      for (int r = 0; r < rows; r += 4) {
-        float4 z[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          z[u] = (r + u < rows) ? __ldg(reinterpret_cast<const float4*>(dZ + (size_t)(m0 + r + u) * lddz + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4* xr = reinterpret_cast<const float4*>(xs[r + u]);
-          const float zz[4] = {z[u].x, z[u].y, z[u].z, z[u].w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) accb[c] += zz[c];
-#pragma unroll
-          for (int q = 0; q < SK / 4; ++q) {
-            const float4 v = xr[q];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              acc[c][4 * q] = fmaf(zz[c], v.x, acc[c][4 * q]); acc[c][4 * q + 1] = fmaf(zz[c], v.y, acc[c][4 * q + 1]);
-              acc[c][4 * q + 2] = fmaf(zz[c], v.z, acc[c][4 * q + 2]); acc[c][4 * q + 3] = fmaf(zz[c], v.w, acc[c][4 * q + 3]);
-            }
-          }
-        }
-      }
-    }
-  }
-  if (n < N) {
-    const float alpha = alpha_p ? __ldg(alpha_p) : 1.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-      for (int k = 0; k < SK; ++k)
-        if (k < K) atomicAdd(dW + (size_t)(n + c) * lddw + k, alpha * acc[c][k]);
-      if (db) atomicAdd(db + n + c, accb[c]);
-    }
-  }
-}
-
 bool skinny_supported(int K) { return K <= SK; }
 
 int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y,
@@ -453,8 +384,8 @@ int launch_skinny_fwd(const float* X, int ldx, const float* W, int ldw, const fl
 int launch_skinny_fwd_emit(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, __half* Yh, int ld_h,
                            uint32_t* tile_amax, int amax_stride, int M, int N, int K, int act, cudaStream_t st) {
   const int col_tiles = ceil_div(N, 256), row_tiles = ceil_div(M, 128);
-  const int gy = max(1, min(row_tiles, kNumSMs / col_tiles));          // persistent: about one 256-thread block per SM
-  skinny_fwd_emit_kernel<<<dim3(col_tiles, gy), 256, 0, st>>>(X, ldx, W, ldw, bias, inv_sigma, Yh, ld_h, tile_amax, amax_stride, M, N, K, act);
+  const int gy = max(1, min(row_tiles, kNumSMs / col_tiles));          // persistent: about one 512-thread block per SM
+  skinny_fwd_emit_kernel<<<dim3(col_tiles, gy), 512, 0, st>>>(X, ldx, W, ldw, bias, inv_sigma, Yh, ld_h, tile_amax, amax_stride, M, N, K, act);
   GCBF_LAUNCH_OK();
   return GCBF_OK;
 }
@@ -485,15 +416,6 @@ int launch_skinny_wgrad(const float* dZ, int lddz, const float* X, int ldx, cons
   if (!accumulate) {
     GCBF_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)K * 4, N, st));
     if (db) GCBF_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * 4, st));
-  }
-  if ((N & 3) == 0 && (lddz & 3) == 0 && (reinterpret_cast<uintptr_t>(dZ) & 15) == 0 && N >= 1024) {
-    const int col_blocks = ceil_div(N, 1024);
-    int row_blocks = max(1, min(ceil_div(M, 4 * SK_ROWS), (2 * kNumSMs) / col_blocks));   // two resident blocks per SM; few blocks = few final atomics
-    const int rpb = ceil_div(ceil_div(M, row_blocks), SK_ROWS) * SK_ROWS;
-    row_blocks = ceil_div(M, rpb);
-    skinny_wgrad4_kernel<<<dim3(col_blocks, row_blocks), 256, 0, st>>>(dZ, lddz, X, ldx, inv_sigma, dW, lddw, db, M, N, K, rpb);
-    GCBF_LAUNCH_OK();
-    return GCBF_OK;
   }
   const int col_blocks = ceil_div(N, 256);
   int row_blocks = max(1, min(ceil_div(M, 4 * SK_ROWS), (4 * kNumSMs) / col_blocks));
