@@ -12,7 +12,10 @@
  *   - nothing here allocates or synchronises: outputs / workspaces are caller-provided, every launch
  *     goes to `stream` (a cudaStream_t passed as void*);
  *   - return value: 0 on success, negative GCBF_E_* on failure; gcbf_last_error() gives the text;
- *   - thread-compatible: no global mutable state except the per-thread last-error string.
+ *   - per-kernel entry points are thread-compatible (no global mutable state except the per-thread last-error string); the
+ *     chain-level entry points of ABI v3 keep per-process state (seven CUDA events and one pinned word per device for the train
+ *     step's streams, the instrumentation records, the gemm-implementation switch) and must be driven from one host thread per
+ *     process -- the deployment model is one process per GPU.
  */
 #ifndef GCBF_B200_H
 #define GCBF_B200_H
