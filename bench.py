@@ -274,6 +274,26 @@ def rollout_leg(cfg_name, dev, steps=20):
             'agent_steps_per_s': round(B * n / (wall / 1e3), 1), 'host_syncs_per_vector_step': 1}
 
 
+def controller_leg(cfg_name, dev, calls=5):
+    """Test-time controller (GCBF.apply = gcbf_apply in csrc/apply.cu) on ONE graph of the config: wall time per call
+    with the reference's settings (lr 0.1, rand 30, up to 31 Adam rounds); random-init weights violate the h_dot condition
+    somewhere, so the refinement loop runs (rounds reported)."""
+    sb, env, algo = build_case(cfg_name, dev, 0)
+    single = env.graph_from_states(sb.states[:sb.nodes_per_graph].to(dev))
+    algo.apply(single)
+    torch.cuda.synchronize()
+    rounds = []
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        algo.apply(single)
+        rounds.append(getattr(algo, 'last_apply_rounds', -1))
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / calls * 1e3
+    per_round = wall / max(1.0, sum(rounds) / len(rounds) + 2)      # + the two passes before the loop
+    return {'workload': f'{cfg_name}: GCBF.apply on one graph ({sb.num_agents} agents, {int(single.edge_index.shape[1])} edges)',
+            'wall_ms_per_call': round(wall, 3), 'adam_rounds': rounds, 'wall_ms_per_round': round(per_round, 3)}
+
+
 def shape_traffic(dom):
     """DRAM bytes per launch of the dominant launch shape from the committed `ncu --set full` capture of exactly that shape
     (profiles/r02_gemm_h_ncu_full.json: {"launches": [{"product", "M", "N", "K", "dram_read_bytes", "dram_write_bytes"}, ...]});
@@ -380,6 +400,7 @@ def run_own(args):
     if world == 1 and not args.no_e2e:
         try:
             line['rollout'] = [rollout_leg(main_cfg, dev), rollout_leg('C1x256', dev)]
+            line['controller'] = [controller_leg('C1', dev), controller_leg(main_cfg, dev)]
         except Exception as ex:                                   # the rollout leg is an extra: never lose the bench line over it
             line['rollout'] = {'error': repr(ex)[:200]}
     if world == 1 and not args.no_cpu_baseline:

@@ -78,6 +78,7 @@ int net_forward(Run& R, const gcbf_net_desc& net, const float* x, const float* e
                 int ld_out, NetCtx* ctx);
 int net_backward(Run& R, const gcbf_net_desc& net, const NetCtx& ctx, const int32_t* rowptr, const int64_t* row_index,
                  const float* d_out, int ld_dout, float* d_edge_attr, bool skip_wgrad, cudaEvent_t gamma_done = nullptr);
+int check_step(const gcbf_step_desc* d, const gcbf_step_batch* b, const char* what);   // step.cu
 int vec_add(Run& R, float* dst, const float* src, int64_t n);
 size_t net_fwd_bytes(const gcbf_net_desc& net, int64_t E, int Nn, int rows, bool has_row_index, bool save);
 size_t net_bwd_bytes(const gcbf_net_desc& net, int64_t E, int Nn, int rows, bool has_row_index, bool need_d_edge_attr, bool skip_wgrad);

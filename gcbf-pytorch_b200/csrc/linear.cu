@@ -23,6 +23,9 @@ int launch_fewrows_fwd(const float* X, int ldx, const float* W, int ldw, const f
                        int N, int K, int act, cudaStream_t st);
 int launch_fewrows_dgrad(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src, int ld_relu,
                          float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
+bool fewrows_narrow_supported(int M, int N, int K);
+int launch_fewrows_dgrad_narrow(const float* dZ, int lddz, const float* W, int ldw, const float* inv_sigma, const float* relu_src, int ld_relu,
+                                float* dX, int lddx, int M, int N, int K, int accumulate, cudaStream_t st);
 int launch_fewrows_wgrad(const float* dZ, int lddz, const float* X, int ldx, const float* inv_sigma, float* dW, int lddw, float* db, int M, int N,
                          int K, int accumulate, cudaStream_t st);
 int launch_tiny_fwd(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* inv_sigma, float* Y, int ldy,
@@ -99,6 +102,10 @@ extern "C" int gcbf_linear_bwd_data(const float* dZ, int lddz, const float* W, i
   if (impl == 0 && fewrows_supported(M, K, N)) {
     g_last_impl = 5;
     return launch_fewrows_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
+  }
+  if (impl == 0 && fewrows_narrow_supported(M, N, K)) {            // M <= 64 rows, K <= 32 inputs: d edge_attr of a single small graph
+    g_last_impl = 5;
+    return launch_fewrows_dgrad_narrow(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);
   }
   g_last_impl = 1;
   return launch_simt_dgrad(dZ, lddz, W, ldw, inv_sigma, relu_src, ld_relu, dX, lddx, M, N, K, accumulate, st);

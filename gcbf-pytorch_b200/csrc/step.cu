@@ -54,7 +54,7 @@ static int host_res(HostRes** out) {
   return 0;
 }
 
-static int check_step(const gcbf_step_desc* d, const gcbf_step_batch* b, const char* what) {
+int check_step(const gcbf_step_desc* d, const gcbf_step_batch* b, const char* what) {
   if (!d || !b) { set_error("%s: null descriptor", what); return GCBF_E_INVALID; }
   if (int rc = check_net(&d->cbf)) return rc;
   if (int rc = check_net(&d->actor)) return rc;

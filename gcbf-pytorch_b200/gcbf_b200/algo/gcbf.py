@@ -49,37 +49,37 @@ class _FlatBucket:
     """All parameters of a list of modules re-homed into one flat fp32 buffer (and their .grad into a second
     one), so the gradient all-reduce is a single collective and clip+Adam a single pass per net."""
 
+    ALIGN = 64          # floats: every parameter starts on a 256-byte boundary (16-byte vector loads / cp.async / TMA of the weight
+                        # matrices; without it the 1-element bias of the gate's last layer shifts every later matrix by 4 bytes)
+
     def __init__(self, modules: List[nn.Module], device):
-        self.ranges = []
-        params = []
+        up = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.ranges, self.tail_start = [], []
+        params, offsets = [], []
+        off = 0
         for m in modules:
-            ps = [p for p in m.parameters()]
-            start = sum(p.numel() for p in params)
-            params += ps
-            self.ranges.append((start, sum(p.numel() for p in params)))
-        total = sum(p.numel() for p in params)
-        self.flat = torch.empty(total, device=device, dtype=torch.float32)
+            start, tail = off, None
+            for name, p in m.named_parameters():
+                # where the [gamma + head] parameters of the net start (parameters() order: gate_nn, phi, gamma, head): that tail of
+                # a net's range is final before the E-row phi / gate backward has run, so its all-reduce can start early
+                if '.gamma.' in name and tail is None:
+                    tail = off
+                params.append(p)
+                offsets.append(off)
+                off += up(p.numel())
+            self.ranges.append((start, off))
+            self.tail_start.append(off if tail is None else tail)
+        total = off
+        self.flat = torch.zeros(total, device=device, dtype=torch.float32)      # the padding stays zero: zero gradient, zero Adam update
         self.grad = torch.zeros(total, device=device, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=device, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=device, dtype=torch.float32)
-        off = 0
-        for p in params:
+        for p, o in zip(params, offsets):
             n = p.numel()
-            self.flat[off:off + n].copy_(p.data.reshape(-1))
-            p.data = self.flat[off:off + n].view(p.shape)
-            p.grad = self.grad[off:off + n].view(p.shape)
-            off += n
-        self.params = params
-        # where the [gamma + head] parameters of each net start (parameters() order: gate_nn, phi, gamma, head): that tail of a
-        # net's range is final before the E-row phi / gate backward has run, so its all-reduce can start early
-        self.tail_start = []
-        for m, (lo, hi) in zip(modules, self.ranges):
-            off, tail = lo, hi
-            for name, p_ in m.named_parameters():
-                if '.gamma.' in name and tail == hi:
-                    tail = off
-                off += p_.numel()
-            self.tail_start.append(tail)
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view(p.shape)
+            p.grad = self.grad[o:o + n].view(p.shape)
+        self.params, self.offsets = params, offsets
         self.sumsq = torch.zeros(len(modules), device=device, dtype=torch.float64)
         self.step = 0
 
@@ -293,14 +293,13 @@ class GCBF(Algorithm):
         self._native_desc = (key, (d, keep, cbf_spec.all_layers(), act_spec.all_layers()))
         return self._native_desc[1]
 
-    def _train_step_native(self, graphs, apply_optim: bool, compute_acc_h_dot: bool) -> Dict[str, Tensor]:
+    def _native_inputs(self, graphs):
+        """(gcbf_step_desc, gcbf_step_batch, tensors the two point into, layer lists, M, E) for a batch of graphs: what every
+        chain-level call of the library takes."""
         import ctypes
         from .. import native
         from ..nn.gnn import cached_rowptr
         env = self._env
-        bucket = self._ensure_bucket()
-        red = self._reducer()
-        dev = graphs.states.device
         d, _keep, cbf_layers, act_layers = self._step_desc()
         ops.sync_gemm_impl()
         d.cbf.refresh_weights = 1 if native._weights_stale(cbf_layers) else 0
@@ -313,6 +312,7 @@ class GCBF(Algorithm):
             gpg, ldg = ops._mat(goal_pg.contiguous())
             d.goal, d.ld_goal, d.goal_per_graph = gpg.data_ptr(), ldg, 1
         else:
+            gpg = None
             d.goal, d.ld_goal, d.goal_per_graph = _keep[0].data_ptr(), ops._mat(_keep[0])[1], 0
         st, ld = ops._mat(graphs.states.detach())
         x, ea, ei = graphs.x.contiguous(), graphs.edge_attr.detach().contiguous(), graphs.edge_index.contiguous()
@@ -325,6 +325,15 @@ class GCBF(Algorithm):
         b.edge_attr, b.edge_index = (ea.data_ptr(), ei.data_ptr()) if E else (None, None)
         b.rowptr, b.u_ref, b.row_index = rowptr.data_ptr(), uref.data_ptr(), (rows.data_ptr() if rows is not None else None)
         b.num_edges, b.num_nodes, b.num_agents_total = E, int(x.shape[0]), M
+        return d, b, (gpg, st, x, ea, ei, uref, rows, rowptr), cbf_layers, act_layers, M, E
+
+    def _train_step_native(self, graphs, apply_optim: bool, compute_acc_h_dot: bool) -> Dict[str, Tensor]:
+        import ctypes
+        from .. import native
+        bucket = self._ensure_bucket()
+        red = self._reducer()
+        dev = graphs.states.device
+        d, b, _alive, cbf_layers, act_layers, M, E = self._native_inputs(graphs)
         bufs = getattr(self, '_native_ws', None)
         if bufs is None:
             bufs = self._native_ws = (native.GrowBuffer(), native.GrowBuffer())
@@ -467,6 +476,8 @@ class GCBF(Algorithm):
         actions through forward_graph -> CBF (same kernels as training: K2, K3, K4, K5 forward and input-gradient),
         plus the reference's gradient noise `rand * lr * randn * grad`.  The per-agent optimisers are kept as one
         vectorised state (m, v, step count per agent); the O(num_agents) arithmetic around the kernels is host glue."""
+        if ops.NATIVE and data.states.is_cuda:
+            return self._apply_native(data, rand, max_iter)
         env, alpha, lr = self._env, float(self.params['alpha']), 0.1
         dt = float(env.dt)
         with torch.no_grad():
@@ -478,6 +489,7 @@ class GCBF(Algorithm):
             act = torch.where((viol <= 0).unsqueeze(1), nominal, action).clone()
         m, v = torch.zeros_like(act), torch.zeros_like(act)
         t = torch.zeros(act.shape[0], device=act.device)
+        noise = torch.randn(max_iter + 1, *act.shape, device=act.device) if rand else None     # one draw, like the library path
         it = 0
         while True:
             a = act.clone().requires_grad_(True)
@@ -487,7 +499,6 @@ class GCBF(Algorithm):
             if float(loss.detach()) <= 0 or it > max_iter:
                 return a.detach()
             sel = (max_val.detach().reshape(-1) != 0)
-            from .. import ops
             ops.SKIP_WGRAD = True           # only d loss / d action is needed: skip every weight-gradient GEMM
             try:
                 (g,) = torch.autograd.grad(loss, a)
@@ -502,8 +513,35 @@ class GCBF(Algorithm):
                 bc2 = (1 - 0.999 ** t).clamp(min=1e-30).unsqueeze(1)
                 act = torch.where(s2, act - (lr / bc1) * m / (v.sqrt() / bc2.sqrt() + 1e-8), act)
                 if rand:
-                    act = torch.where(s2, act - rand * lr * torch.randn_like(g) * g, act)
+                    act = torch.where(s2, act - rand * lr * noise[it] * g, act)
             it += 1
+
+    def _apply_native(self, data, rand: Optional[float], max_iter: int) -> Tensor:
+        """The same controller as ONE library call (gcbf_apply, csrc/apply.cu): the whole refinement loop, the per-agent Adam
+        kernel and the termination test run inside the library; this method only draws the noise and hands over pointers."""
+        import ctypes
+        from .. import native
+        dev = data.states.device
+        d, b, _alive, cbf_layers, act_layers, M, E = self._native_inputs(data)
+        a = self.action_dim
+        need = native.fn('gcbf_apply_workspace_bytes')(ctypes.byref(d), ctypes.byref(b))
+        if need == 0:
+            native.check(-1, 'gcbf_apply_workspace_bytes')
+        buf = getattr(self, '_apply_ws', None)
+        if buf is None:
+            buf = self._apply_ws = native.GrowBuffer()
+        ws = buf.get(need, dev)
+        rand = float(rand) if rand else 0.0
+        noise = torch.randn(max_iter + 1, M, a, device=dev) if rand else None      # gcbf.py:305 draws randn_like per agent and round
+        action = torch.empty(M, a, device=dev)
+        rounds = ctypes.c_int(0)
+        native.check(native.fn('gcbf_apply')(ctypes.byref(d), ctypes.byref(b), 0.1, rand, noise.data_ptr() if noise is not None else None,
+                                            int(max_iter), action.data_ptr(), a, ctypes.byref(rounds), ws.data_ptr(), ws.numel(),
+                                            _C.stream()), 'gcbf_apply')
+        native._mark_fresh(cbf_layers)
+        native._mark_fresh(act_layers)
+        self.last_apply_rounds = rounds.value
+        return action
 
     # ---- checkpoints (file names and keys of gcbf.py:249-258) ------------------------------------------
     def save(self, save_dir: str):

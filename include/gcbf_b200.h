@@ -420,6 +420,18 @@ int gcbf_step_relink(const gcbf_step_desc* d, const gcbf_step_batch* b, gcbf_ste
 int gcbf_step_backward(const gcbf_step_desc* d, const gcbf_step_batch* b, gcbf_step_ctx* ctx, gcbf_step_out* out, void* const* events,
                        void* stream, void* side_stream);
 
+/* GCBF.apply, the test-time controller (gcbf/algo/gcbf.py:260-309; what gcbf/trainer/trainer.py:124 and test.py run), for ONE graph
+ * (d->env.num_graphs == 1): the actor's action where the nominal zero action violates the h_dot condition, then up to max_iter + 1
+ * rounds of forward_graph -> CBF -> d mean(relu(-h_dot - alpha h)) / d action and one Adam(lr) step per violating agent (the
+ * reference's per-agent optimisers as one kernel), plus `action -= rand * lr * noise * grad` (gcbf.py:305) with the caller's standard
+ * normals noise[(max_iter + 1), num_agents, action_dim] (NULL allowed when rand == 0).  Uses d->cbf, d->actor, d->env, goal / gain,
+ * alpha, action_dim, state_dim; ignores the loss coefficients and the gradient bucket (no weight gradient is computed).  One host sync
+ * per round (the violating-agent count, as the reference's `if loss_h_dot <= 0`).  action [num_agents, action_dim] (pitch ld_action);
+ * *iterations (host, optional) = Adam rounds done. */
+size_t gcbf_apply_workspace_bytes(const gcbf_step_desc* d, const gcbf_step_batch* graph);
+int gcbf_apply(const gcbf_step_desc* d, const gcbf_step_batch* graph, float lr, float rand, const float* noise, int max_iter,
+               float* action, int ld_action, int* iterations, void* workspace, size_t workspace_bytes, void* stream);
+
 /* instrumentation (bench.py): kernels launched by the chain-level calls since the last reset, and optional CUDA-event timing of
  * every linear-layer launch (kind 0 forward / 1 data-grad / 2 weight-grad on the tensor cores, 3 fp32 linear kernels, 4 operand
  * preparation = amax + fp16 split) */

@@ -72,9 +72,14 @@ def _worker(rank, world, port, tmp):
         ref = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
         ref.load_state_dict(net.state_dict())
         ref(x).square().sum().backward()
-        flat_ref = torch.cat([p_.grad.reshape(-1) for p_ in ref.parameters()])
-        assert torch.allclose(bucket.grad, flat_ref, rtol=1e-5, atol=1e-6)
-        assert bucket.ranges == [(0, 15), (15, 23)]
+        # layout: every parameter on a 256-byte boundary (64 floats), zero padding in between, module ranges back to back
+        assert bucket.offsets == [0, 64, 128, 192] and bucket.ranges == [(0, 128), (128, 256)] and bucket.grad.numel() == 256
+        used = torch.zeros(256, dtype=torch.bool)
+        for p_, q_, o in zip(net.parameters(), ref.parameters(), bucket.offsets):
+            assert p_.data_ptr() == bucket.flat.data_ptr() + 4 * o
+            assert torch.allclose(bucket.grad[o:o + q_.numel()], q_.grad.reshape(-1), rtol=1e-5, atol=1e-6)
+            used[o:o + q_.numel()] = True
+        assert bucket.grad[~used].abs().sum() == 0 and bucket.flat[~used].abs().sum() == 0
         torch.save(bucket.grad.clone(), os.path.join(tmp, f'g{rank}.pt'))
     finally:
         dist.destroy_process_group()

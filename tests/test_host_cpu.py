@@ -141,7 +141,8 @@ def test_flat_bucket_views_survive_load_state_dict():
     algo = make_algo('gcbf', env, 4, 4, 4, 2, dev)
     b = algo._ensure_bucket()
     n_params = sum(p.numel() for p in algo.cbf.parameters()) + sum(p.numel() for p in algo.actor.parameters())
-    assert b.flat.numel() == n_params
+    assert n_params <= b.flat.numel() < n_params + 64 * len(b.params)       # every parameter starts on a 256-byte boundary
+    assert all(o % 64 == 0 for o in b.offsets)
     sd = {k: v.clone() + 1 for k, v in algo.cbf.state_dict().items()}
     algo.cbf.load_state_dict(sd)
     p0 = next(algo.cbf.parameters())
@@ -359,6 +360,45 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
     assert lib.gcbf_sn_power_iter_batched(None, 1, ok_ptr, 0, None) == -1
     # the fp32 entry points keep their "tensor-core path has its own entry point" answer for impl = 2
     assert lib.gcbf_linear_fwd(ok_ptr, 64, ok_ptr, 64, None, None, ok_ptr, 64, 0, 64, 64, 0, 2, None, None) in (0, -3)
+
+
+def test_apply_entry_point_without_a_gpu():
+    """gcbf_apply (the test-time controller as one library call): the workspace query replays the call without launching, and
+    the argument checks run before any CUDA call -- one graph only, noise required when rand != 0, aligned workspace."""
+    from gcbf_b200 import synth
+    from gcbf_b200.synth import seeded_algo
+    sb = synth.make_states('DubinsCar', 16, 4, 1, 2.0, 1)
+    env, algo = seeded_algo(sb.env, sb.num_agents, torch.device('cpu'), 0, {'num_obs': sb.num_obs, 'area_size': sb.area_size})
+    env.set_goal(sb.goals)
+    d = algo._step_desc()[0]
+
+    def batch(B, E=300):
+        cfg_s = env._cfg(B)
+        ctypes.memmove(ctypes.byref(d.env), ctypes.byref(cfg_s), ctypes.sizeof(_C.EnvCfg))
+        b = native.StepBatch()
+        fake = 1 << 20
+        b.states, b.ld_state, b.x, b.edge_attr, b.edge_index, b.rowptr, b.u_ref = fake, env.state_dim, fake, fake, fake, fake, fake
+        b.row_index = fake
+        b.num_edges, b.num_nodes, b.num_agents_total = E, B * sb.nodes_per_graph, B * sb.num_agents
+        return b
+
+    b1 = batch(1)
+    need = native.fn('gcbf_apply_workspace_bytes')(ctypes.byref(d), ctypes.byref(b1))
+    assert need > 0, _C.lib().gcbf_last_error()
+    bigger = native.fn('gcbf_apply_workspace_bytes')(ctypes.byref(d), ctypes.byref(batch(1, 3000)))
+    assert bigger > need
+    b1 = batch(1)
+    call = native.fn('gcbf_apply')
+    rounds = ctypes.c_int(0)
+    ok = 0x7f0000000000
+    assert call(ctypes.byref(d), ctypes.byref(b1), 0.1, 30.0, None, 30, ok, 2, ctypes.byref(rounds), ok, need, None) == -1     # rand without noise
+    assert 'noise' in _C.lib().gcbf_last_error().decode()
+    assert call(ctypes.byref(d), ctypes.byref(b1), 0.1, 0.0, None, 30, ok, 1, ctypes.byref(rounds), ok, need, None) == -1      # pitch < action_dim
+    assert call(ctypes.byref(d), ctypes.byref(b1), 0.1, 0.0, None, 30, ok, 2, ctypes.byref(rounds), ok + 8, need, None) == -1  # misaligned workspace
+    assert call(ctypes.byref(d), ctypes.byref(b1), 0.1, 0.0, None, 30, ok, 2, ctypes.byref(rounds), ok, 1024, None) == native.E_WORKSPACE
+    b2 = batch(2)
+    assert call(ctypes.byref(d), ctypes.byref(b2), 0.1, 0.0, None, 30, ok, 2, ctypes.byref(rounds), ok, need * 4, None) == -1  # two graphs
+    assert 'one graph' in _C.lib().gcbf_last_error().decode()
 
 
 def test_abi_struct_mirrors_and_workspace_queries_without_a_gpu():

@@ -622,7 +622,8 @@ def rel_err(a, b):
     return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-300)).item()
 
 
-@pytest.mark.parametrize('M,N,K', [(16, 2048, 2048), (44, 2048, 260), (1, 512, 1024), (64, 128, 32), (45, 256, 2048), (16, 1024, 1027), (33, 70, 130)])
+@pytest.mark.parametrize('M,N,K', [(16, 2048, 2048), (44, 2048, 260), (1, 512, 1024), (64, 128, 32), (45, 256, 2048), (16, 1024, 1027), (33, 70, 130),
+                                   (64, 2048, 2048), (57, 1024, 520), (3, 256, 128), (44, 2052, 516)])
 def test_linear_few_rows(M, N, K):
     """M <= 64 (rollout-time single-graph passes, config C1): weight-streaming kernels (gemm_fewrows.cu) instead of a 128 x 128 tile
     grid; exact fp32 FFMA, forward with fused bias / activation, data-grad with ReLU mask and accumulate, weight-grad + bias grad."""
@@ -637,7 +638,7 @@ def test_linear_few_rows(M, N, K):
     assert _C.lib().gcbf_last_gemm_impl() == 5
     assert am.view(torch.float32).item() == y.abs().max().item()
     dx = ops.linear_bwd_data(dzd, Wd, alpha, rsd)
-    assert _C.lib().gcbf_last_gemm_impl() == (5 if K >= 64 and N >= 32 else 1)      # (output width K, contraction N)
+    assert _C.lib().gcbf_last_gemm_impl() == (5 if (K >= 64 and N >= 32) or (K <= 32 and N >= 64) else 1)      # (output width K, contraction N)
     dx_acc = torch.ones(M, K, device=DEV)
     ops.linear_bwd_data(dzd, Wd, None, None, out=dx_acc, accumulate=True)
     dW, db = ops.linear_bwd_weight(dzd, xd, alpha)
@@ -653,3 +654,21 @@ def test_linear_few_rows(M, N, K):
     assert e(dW, 1.2 * (dz64.t() @ x64)) < 2e-6
     assert e(dW_acc, dz64.t() @ x64 + 1) < 2e-6
     assert e(db, dz64.sum(0)) < 1e-5 and e(db_acc, dz64.sum(0) + 1) < 1e-5
+
+
+@pytest.mark.parametrize('M,N,K', [(44, 2048, 13), (16, 2048, 12), (64, 512, 32), (2, 64, 3)])
+def test_linear_few_rows_narrow_input_grad(M, N, K):
+    """d(input) of a layer with <= 32 inputs on <= 64 rows (d edge_attr of one small graph: the first phi layer in GCBF.apply): one block
+    per row instead of the single-block tile kernel (213 us in the launch list of one apply round)."""
+    g = _g(M + N + K)
+    W, dz, rs = torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(M, N, generator=g), torch.randn(M, K, generator=g)
+    Wd, dzd, rsd = W.to(DEV), dz.to(DEV), rs.to(DEV)
+    alpha = torch.tensor([0.7], device=DEV)
+    dx = ops.linear_bwd_data(dzd, Wd, alpha, rsd)
+    assert _C.lib().gcbf_last_gemm_impl() == 5
+    dx_acc = torch.ones(M, K, device=DEV)
+    ops.linear_bwd_data(dzd, Wd, None, None, out=dx_acc, accumulate=True)
+    want = dzd.double() @ Wd.double()
+    e = lambda a, r: ((a.double() - r).abs().max() / r.abs().max()).item()
+    assert e(dx, 0.7 * want * (rsd > 0)) < 2e-6
+    assert e(dx_acc, want + 1) < 2e-6

@@ -165,3 +165,33 @@ def test_abi_struct_mirrors_match_the_library():
                native.MlpCtx, native.StepCtx, native.TimeRec, _C.SnLayer, _C.SplitDesc, native.H16Desc]
     for i, m in enumerate(mirrors):
         assert ctypes.sizeof(m) == _C.lib().gcbf_abi_struct_size(i), m.__name__
+
+
+@pytest.mark.parametrize('env_name,n,obs,area,rand,max_iter', [('DubinsCar', 16, 4, 2.0, 0, 30), ('SimpleCar', 8, 0, 1.5, 0, 30),
+                                                               ('SimpleDrone', 8, 8, 1.0, 0, 30), ('DubinsCar', 16, 4, 2.0, 30, 2),
+                                                               ('SimpleCar', 4, 0, 50.0, 0, 5)])
+def test_apply_matches_python_sequencing(env_name, n, obs, area, rand, max_iter):
+    """gcbf_apply (csrc/apply.cu: the whole refinement loop + the per-agent Adam kernel in the library) against the Python-sequenced
+    controller (autograd over the per-kernel ops), same weights, same noise draw.  Adam's normalised step amplifies rounding
+    where a gradient component is ~0, hence the tolerance; with noise only a few rounds are compared.  Last case: no edges."""
+    outs = []
+    try:
+        for nat in (False, True):
+            sb, env, algo, data = _setup(env_name, n, obs, 1, area, 91)
+            ops.NATIVE = nat
+            single = env.graph_from_states(sb.states[:sb.nodes_per_graph].to(DEV))
+            torch.manual_seed(7)
+            a = algo.apply(single, rand=rand, max_iter=max_iter)
+            torch.cuda.synchronize()
+            outs.append((a.clone(), [v.clone() for k, v in algo.cbf.state_dict().items() if k.endswith(('_u', '_v'))],
+                         getattr(algo, 'last_apply_rounds', None)))
+    finally:
+        ops.NATIVE = True
+    (pa, puv, _), (na, nuv, rounds) = outs
+    assert rounds is not None and 0 <= rounds <= max_iter + 1
+    assert na.shape == pa.shape
+    assert (na - pa).abs().max().item() <= 2e-3 * max(1.0, pa.abs().max().item()), (na - pa).abs().max().item()
+    if rounds > 0:
+        assert na.abs().max().item() > 0                 # somebody violated: the refined action is not the nominal zero
+    for x, y in zip(puv, nuv):                           # the same number of CBF passes -> the same number of power iterations
+        assert torch.allclose(x, y, atol=1e-5)
