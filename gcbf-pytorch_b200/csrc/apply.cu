@@ -11,6 +11,8 @@
 // one kernel updates every violating agent.  Each round costs one host sync (the violating-agent count decides whether the backward is
 // launched at all), like the reference's `if loss_h_dot <= 0` [:294].  Every CBF pass advances the spectral-norm vectors (the reference
 // never calls .eval()).
+#include <cstdlib>
+
 #include "chain.h"
 
 namespace gcbf {
@@ -45,15 +47,18 @@ __global__ void apply_viol_kernel(const float* __restrict__ h, const float* __re
   }
   const unsigned b = __ballot_sync(0xffffffffu, on);
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
+  if (i == 0) count[1] += 1;      // rounds evaluated so far: the Adam kernel of this round reads noise slice count[1] - 1
 }
 
 // torch.optim.Adam(lr, betas (0.9, 0.999), eps 1e-8) on the rows with max_val != 0, each with its own step count, then
 // action -= rand * lr * noise * grad  (gcbf.py:301-305)
 __global__ void agent_adam_kernel(float* __restrict__ act, float* __restrict__ m, float* __restrict__ v, float* __restrict__ t,
-                                  const float* __restrict__ g, const float* __restrict__ max_val, const float* __restrict__ noise, int M,
-                                  int a, float lr, float rand) {
+                                  const float* __restrict__ g, const float* __restrict__ max_val, const float* __restrict__ noise_all,
+                                  const int* __restrict__ rounds, int M, int a, float lr, float rand) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per agent (= per reference optimiser)
   if (r >= M || max_val[r] == 0.f) return;
+  // this round's slice of the noise: the round index lives on the device so that the launch is identical every round (CUDA graph)
+  const float* noise = noise_all ? noise_all + (size_t)(rounds[1] - 1) * M * a : nullptr;
   const float step = t[r] + 1.f;
   t[r] = step;
   const double bc1 = 1.0 - pow(0.9, (double)step), bc2 = 1.0 - pow(0.999, (double)step);
@@ -135,30 +140,87 @@ static int apply_run(Run& R, const gcbf_step_desc& d, const gcbf_step_batch& b, 
     GCBF_LAUNCH_OK();
     R.launched(2);
   }
-  int it = 0;
-  for (;; ++it) {
-    NetCtx ctx;
-    if (int rc = apply_forward(R, d, b, cbf_again, B, B.act, &ctx)) return rc;                                                                         // :288-290
+  // One round = two launch sequences around the host's look at the violating-agent count.  Every round of a call launches exactly the
+  // same kernels on the same pointers (the workspace is rewound, the noise slice is picked on the device), so round 1 is captured into
+  // two CUDA graphs that rounds 2.. replay: ~75 dependent launches of a few microseconds each become two graph launches.  Round 0 runs
+  // eagerly (one-time attribute / descriptor set-up happens there); GCBF_APPLY_GRAPH=0, per-launch timing or a failed capture keep the
+  // eager path.
+  NetCtx ctx;
+  auto round_fwd = [&]() -> int {
+    if (int rc = apply_forward(R, d, b, cbf_again, B, B.act, &ctx)) return rc;                                                                          // :288-290
     if (!R.dry) {
       CHAIN_CUDA(cudaMemsetAsync(B.count, 0, 4, R.st));
-      apply_viol_kernel<<<grid_m, 256, 0, R.st>>>(B.h, B.hn, B.max_val, B.d_hn, B.count, M, dt, d.alpha);                                                // :291-293
+      apply_viol_kernel<<<grid_m, 256, 0, R.st>>>(B.h, B.hn, B.max_val, B.d_hn, B.count, M, dt, d.alpha);                                               // :291-293
       GCBF_LAUNCH_OK();
       CHAIN_CUDA(cudaMemcpyAsync(g_pinned_count, B.count, 4, cudaMemcpyDeviceToHost, R.st));
-      CHAIN_CUDA(cudaStreamSynchronize(R.st));
       R.launched(2);
-      if (*g_pinned_count == 0 || it > max_iter) break;                                                                                                 // :294
     }
-    if (int rc = net_backward(R, cbf_again, ctx, b.rowptr, b.row_index, B.d_hn, 1, B.d_ea, true)) return rc;                                             // :300 (no weight gradient)
+    return 0;
+  };
+  auto round_bwd = [&]() -> int {
+    if (int rc = net_backward(R, cbf_again, ctx, b.rowptr, b.row_index, B.d_hn, 1, B.d_ea, true)) return rc;                                            // :300 (no weight gradient)
     peak = peak > R.ws.off ? peak : R.ws.off;
     R.ws.off = mark0;
-    if (R.dry) break;
+    if (R.dry) return 0;
     CHAIN_CUDA(cudaMemsetAsync(B.d_states, 0, (size_t)Nn * s * 4, R.st));
     CHAIN_CALL(gcbf_edge_attr_bwd(d.env.env, B.states_next, s, b.edge_index, E, B.d_ea, B.d_states, R.st));
     CHAIN_CALL(gcbf_step_bwd(&cfg, B.d_states, s, B.pass_mask, B.g, R.st));
-    agent_adam_kernel<<<grid_m, 256, 0, R.st>>>(B.act, B.m, B.v, B.t, B.g, B.max_val, noise ? noise + (size_t)it * M * a : nullptr, M, a, lr, rand);   // :301-305
+    agent_adam_kernel<<<grid_m, 256, 0, R.st>>>(B.act, B.m, B.v, B.t, B.g, B.max_val, noise, B.count, M, a, lr, rand);                                  // :301-305
     GCBF_LAUNCH_OK();
     R.launched(E ? 4 : 3);
+    return 0;
+  };
+  struct Captured { cudaGraphExec_t exec = nullptr; long long launches = 0; } gf, gb;
+  bool graphs = !R.dry && !timing_on() && max_iter >= 3;
+  if (graphs) { const char* e = getenv("GCBF_APPLY_GRAPH"); graphs = !(e && e[0] == '0'); }
+  // runs `body` under stream capture, instantiates and launches the result; on any capture problem falls back to running it eagerly
+  auto capture_and_launch = [&](Captured& c, auto& body) -> int {
+    const long long before = g_launches.load(std::memory_order_relaxed);
+    const size_t off_before = R.ws.off;
+    bool ok = cudaStreamBeginCapture(R.st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    int rc = 0;
+    if (ok) {
+      rc = body();
+      cudaGraph_t graph = nullptr;
+      ok = (cudaStreamEndCapture(R.st, &graph) == cudaSuccess) && rc == 0 && graph != nullptr;
+      if (ok) ok = cudaGraphInstantiate(&c.exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      c.launches = g_launches.load(std::memory_order_relaxed) - before;
+    }
+    if (!ok) {
+      (void)cudaGetLastError();
+      if (c.exec) { cudaGraphExecDestroy(c.exec); c.exec = nullptr; }
+      graphs = false;
+      g_launches.store(before, std::memory_order_relaxed);
+      R.ws.off = off_before;
+      return body();                       // nothing of the captured sequence has run: run it now
+    }
+    CHAIN_CUDA(cudaGraphLaunch(c.exec, R.st));
+    return 0;
+  };
+  auto cleanup = [&]() {
+    if (gf.exec) cudaGraphExecDestroy(gf.exec);
+    if (gb.exec) cudaGraphExecDestroy(gb.exec);
+  };
+  if (!R.dry) CHAIN_CUDA(cudaMemsetAsync(B.count, 0, 8, R.st));      // [0] violating agents of the round, [1] rounds evaluated
+  int it = 0;
+  for (;; ++it) {
+    int rc = 0;
+    if (graphs && gf.exec) { rc = cudaGraphLaunch(gf.exec, R.st) == cudaSuccess ? 0 : GCBF_E_CUDA; R.launched((int)gf.launches); }
+    else if (graphs && it == 1) rc = capture_and_launch(gf, round_fwd);
+    else rc = round_fwd();
+    if (rc) { cleanup(); return rc; }
+    if (!R.dry) {
+      if (cudaStreamSynchronize(R.st) != cudaSuccess) { cleanup(); set_error("gcbf_apply: %s", cudaGetErrorString(cudaGetLastError())); return GCBF_E_CUDA; }
+      if (*g_pinned_count == 0 || it > max_iter) break;                                                                                                 // :294
+    }
+    if (graphs && gb.exec) { rc = cudaGraphLaunch(gb.exec, R.st) == cudaSuccess ? 0 : GCBF_E_CUDA; R.launched((int)gb.launches); }
+    else if (graphs && it == 1) rc = capture_and_launch(gb, round_bwd);
+    else rc = round_bwd();
+    if (rc) { cleanup(); return rc; }
+    if (R.dry) break;
   }
+  cleanup();
   R.ws.off = peak;
   if (!R.dry) {
     CHAIN_CUDA(cudaMemcpy2DAsync(action_out, (size_t)ld_action * 4, B.act, (size_t)a * 4, (size_t)a * 4, M, cudaMemcpyDeviceToDevice, R.st));

@@ -72,6 +72,7 @@ struct NetCtx {
 };
 
 bool use_h(int M, int N, int K);
+bool timing_on();      // per-launch CUDA-event timing enabled (gcbf_timing_enable): stream capture is skipped then
 int check_net(const gcbf_net_desc* net);
 int net_forward(Run& R, const gcbf_net_desc& net, const float* x, const float* edge_attr, const int64_t* edge_index,
                 const int32_t* rowptr, int64_t E, int Nn, const int64_t* row_index, int rows, const float* head_extra, float* out,

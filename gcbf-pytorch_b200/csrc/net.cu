@@ -19,6 +19,7 @@ namespace chain {
 std::atomic<long long> g_launches{0};
 static int g_gemm_impl = 0;
 static bool g_timing = false;
+bool timing_on() { return g_timing; }
 struct Rec { cudaEvent_t e0, e1; double flops; int kind, M, N, K; };
 static std::vector<Rec> g_recs;
 static std::vector<cudaEvent_t> g_event_pool;

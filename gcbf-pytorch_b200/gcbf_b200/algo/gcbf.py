@@ -535,9 +535,18 @@ class GCBF(Algorithm):
         noise = torch.randn(max_iter + 1, M, a, device=dev) if rand else None      # gcbf.py:305 draws randn_like per agent and round
         action = torch.empty(M, a, device=dev)
         rounds = ctypes.c_int(0)
-        native.check(native.fn('gcbf_apply')(ctypes.byref(d), ctypes.byref(b), 0.1, rand, noise.data_ptr() if noise is not None else None,
-                                            int(max_iter), action.data_ptr(), a, ctypes.byref(rounds), ws.data_ptr(), ws.numel(),
-                                            _C.stream()), 'gcbf_apply')
+        # the library captures a round into CUDA graphs and replays it; capture is impossible on the legacy default stream, so the call
+        # runs on a stream of its own, ordered after and before the caller's stream
+        cur = torch.cuda.current_stream(dev)
+        st = getattr(self, '_apply_stream', None)
+        if st is None or st.device != dev:
+            st = self._apply_stream = torch.cuda.Stream(dev)
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            rc = native.fn('gcbf_apply')(ctypes.byref(d), ctypes.byref(b), 0.1, rand, noise.data_ptr() if noise is not None else None,
+                                         int(max_iter), action.data_ptr(), a, ctypes.byref(rounds), ws.data_ptr(), ws.numel(), st.cuda_stream)
+        cur.wait_stream(st)
+        native.check(rc, 'gcbf_apply')
         native._mark_fresh(cbf_layers)
         native._mark_fresh(act_layers)
         self.last_apply_rounds = rounds.value
