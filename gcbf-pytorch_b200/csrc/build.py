@@ -33,6 +33,8 @@ def build(force=False, verbose=True, extra_defs=(), target=None):
     defs = list(extra_defs)
     if os.path.exists(os.path.join(HERE, 'gemm_tcgen05_f16.cu')):
         defs.append('-DGCBF_WITH_TCGEN05')
+        if '-DGCBF_NO_SETMAXNREG' not in defs:
+            defs.append('-DGCBF_SETMAXNREG')     # 12 warps: producer warpgroup at 40 registers, epilogue warpgroups at 232 (no spills)
     procs = []
     objs = []
     for src in sources():

@@ -42,7 +42,12 @@ constexpr int BM = 128;
 constexpr int BK = GCBF_TH_BK;         // K elements per k-block (= one smem stage): 32 (64-byte K-major rows) or 64 (128-byte rows)
 static_assert(BK == 32 || BK == 64, "BK must be 32 or 64");
 constexpr int UMMA_K = 16;             // fp16: 32 bytes of K per instruction
+#ifdef GCBF_SETMAXNREG
+constexpr int EPI_WARP0 = 4;           // warpgroup 0 = warp0 TMA, warp1 MMA, warps 2-3 idle (40 registers each after setmaxnreg.dec);
+                                       // warpgroups 1-2 = the 8 promotion / epilogue warps (232 registers each after setmaxnreg.inc)
+#else
 constexpr int EPI_WARP0 = 2;           // warp0 TMA, warp1 MMA, warps 2..17 promotion / epilogue
+#endif
 #ifndef GCBF_EPI_WARPS
 #define GCBF_EPI_WARPS 8
 #endif
@@ -183,7 +188,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (nkb > 0) {
+  // register re-balancing (GCBF_SETMAXNREG, warpgroup-aligned): 384 threads x 168 registers are allocated at launch; the producer
+  // warpgroup gives back 128 per thread, the two epilogue warpgroups take 64 more each -- the 128 accumulators plus the epilogue's
+  // temporaries fit.  Each role's code follows its own setmaxnreg inside its own branch (ptxas allocates per region).
+  if (warp < EPI_WARP0) {
+#ifdef GCBF_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
+   if (nkb > 0) {
     if (warp == 0) {
       // ===== TMA producer =====
       if (lane == 0) {
@@ -246,8 +258,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
           }
         }
       }
-    } else if (warp >= EPI_WARP0) {
-      // ===== promotion / epilogue warps 2..17: TMEM lane quarter = warp % 4, column quarter = (warp - 2) / 4 =====
+    }
+   }
+  } else {
+#ifdef GCBF_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+#endif
+    if (nkb > 0) {
+      // ===== promotion / epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - EPI_WARP0) / 4 =====
       constexpr int CH = BN / (EPI_WARPS / 4);                 // columns owned by one thread
       constexpr int MODE = A_MN ? EPI_WGRAD : (B_MN ? EPI_DGRAD : EPI_FWD);   // the operand layouts identify the product
       const int lg = warp & 3;
