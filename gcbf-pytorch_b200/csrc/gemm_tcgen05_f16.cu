@@ -105,7 +105,11 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CG;               // B rows (output columns) staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int OUT_STAGE_BYTES = EPI_WARPS * 32 * 128;   // per epilogue warp: one 32 x 32 fp32 (or 32 x 64 fp16) box of the output tile
+#ifndef GCBF_OUT_BUFS
+#define GCBF_OUT_BUFS 2
+#endif
+  static constexpr int OUT_BUFS = GCBF_OUT_BUFS;         // staging boxes per epilogue warp: with two, a box is refilled while the bulk store of the other one still reads
+  static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_BUFS * 32 * 128;   // per box: 32 x 32 fp32 (or 32 x 64 fp16) of the output tile
   static constexpr int STAGES_FIT = (232448 - OUT_STAGE_BYTES - 1024 - 512) / STAGE_BYTES;   // 227 KB per CTA
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, tile-max exchange*/;
@@ -330,7 +334,8 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
         const int row = m0 + lg * 32 + lane;
         const bool row_ok = row < Mo;
-        const uint32_t my_stage = smem_u32(out_stage + (warp - EPI_WARP0) * 4096);
+        const uint32_t my_stage = smem_u32(out_stage + (warp - EPI_WARP0) * (4096 * K::OUT_BUFS));
+        uint32_t box = 0;                                      // which of this warp's staging boxes the next bulk store uses
         const bool need_clean = (EMIT && (ep.emit_h || ep.colsum)) || ep.amax_out;     // out-of-range entries must read as exact zeros
         // ---- pass 1: finish the values in place: alpha, bias, activation / ReLU mask
         float tmax = 0.f;
@@ -429,9 +434,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             } else if (ep.tma_store) {
               // the 32 x 32 chunk leaves through this warp's shared-memory stage as ONE bulk tensor store: full 128-byte rows,
               // asynchronous (the warp does not wait on the memory system), ragged edges clipped by the tensor map
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous chunk has left the stage
+              if (lane == 0) {                                  // the store that used this box last has finished reading it
+                if (K::OUT_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
               __syncwarp();
-              const uint32_t rbase = my_stage + (uint32_t)(lane * 128);
+              const uint32_t sbox = my_stage + box * 4096u;
+              if (K::OUT_BUFS == 2) box ^= 1u;
+              const uint32_t rbase = sbox + (uint32_t)(lane * 128);
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (uint32_t)(((q ^ (lane & 7)) << 4))), "f"(acc[c * 32 + 4 * q]),
@@ -442,7 +452,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
               if (lane == 0) {
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                  reinterpret_cast<uint64_t>(&map_c)),
-                             "r"(my_stage), "r"(col0), "r"(m0 + lg * 32)
+                             "r"(sbox), "r"(col0), "r"(m0 + lg * 32)
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
@@ -479,9 +489,14 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
               if (col0 >= No) continue;                          // warp-uniform
 #pragma unroll 1
               for (int plane = 0; plane < 2; ++plane) {
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                if (lane == 0) {
+                  if (K::OUT_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                  else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
                 __syncwarp();
-                const uint32_t rbase = my_stage + (uint32_t)(lane * 128);
+                const uint32_t sbox = my_stage + box * 4096u;
+                if (K::OUT_BUFS == 2) box ^= 1u;
+                const uint32_t rbase = sbox + (uint32_t)(lane * 128);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {                  // 16-byte unit q of this lane's 128-byte row = columns 8q .. 8q+7
                   uint32_t w[4];
@@ -504,7 +519,7 @@ gemm_h_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 if (lane == 0) {
                   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                    reinterpret_cast<uint64_t>(plane ? &map_ol : &map_oh)),
-                               "r"(my_stage), "r"(col0), "r"(m0 + lg * 32)
+                               "r"(sbox), "r"(col0), "r"(m0 + lg * 32)
                                : "memory");
                   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
