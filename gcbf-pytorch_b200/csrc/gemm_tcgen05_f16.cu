@@ -882,7 +882,10 @@ static int launch_cg(const Operand& A, const Operand& B, float* C, int ldc, int 
   const int tiles_m = ceil_div(Mo, BM * CG), tiles_n = ceil_div(No, BN);   // CG == 2: 256-row pair tiles
   const int kblocks = ceil_div(Kc, BK);
   const bool tiled_operand = ep.a_sr || ep.a_sc || ep.b_sr || ep.b_sc;
-  const int kch = (!A_MN && B_MN && !tiled_operand) ? g_kch_dgrad : g_kch;
+  // data-grad: a K-major tile-scaled A (scale tiles 256 contraction elements wide) is compatible with 256-element chunks; an MN-major
+  // tile-scaled operand (scale rows of 128 contraction elements) is not
+  const int kch = (!A_MN && B_MN && !(ep.b_sr || ep.b_sc)) ? g_kch_dgrad : g_kch;
+  (void)tiled_operand;
   // chunks of kch k-blocks must not straddle splits (tile-scaled operands: a chunk lies inside one scale tile)
   const int kps = ceil_div(ceil_div(kblocks, splits), kch) * kch;
   const int nsplit = ceil_div(kblocks, kps);

@@ -124,9 +124,10 @@ int sn_power_iter(Run& R, const gcbf_linear_desc* const* layers, int n, bool sna
 // companion -- no amax pass, no split pass, no fp32 copy in HBM; the ReLU mask of the backward is read from the hi plane and the
 // bias gradient (column sums of dZ) is accumulated by the producing data-grad epilogue.  GCBF_EPI_H=0 keeps the split kernels.
 static int g_epi_h = -1;
-static int g_epi_h_bwd = 0;      // GCBF_EPI_H_BWD=1: also emit in the backward (data-grad epilogue: mask + companion + column sums).  Measured on
-                                 // the 206 k x 2048 x 2048 layer: forward 3.79 -> 4.05 ms against 0.89 ms of amax + split saved (on by default);
-                                 // data-grad 4.71 -> 6.24 ms against the same 0.89 ms (off by default)
+static int g_epi_h_bwd = 1;      // GCBF_EPI_H_BWD=0: no emission in the backward (data-grad epilogue: mask + companion + column sums).  History of
+                                 // the in-step A/B at C3: with the spilling epilogue of the 10-warp kernel the emitting data-grad cost 4.71 -> 6.24 ms
+                                 // against 0.89 ms of amax + split saved (off); with the 12-warp setmaxnreg kernel, two staging boxes and
+                                 // 256-element chunks for the consumer it is 3.71 -> 3.99 ms: the step gains ~1 ms (on)
 static bool epi_h_enabled() {
   if (g_epi_h < 0) {
     const char* e = getenv("GCBF_EPI_H");
@@ -134,7 +135,7 @@ static bool epi_h_enabled() {
     g_epi_h = (e && e[0] == '0') ? 0 : 1;
     if (k && atoi(k) > 4) g_epi_h = 0;          // tile-scaled operands need promotion chunks of <= 128 K-elements
     const char* b = getenv("GCBF_EPI_H_BWD");
-    g_epi_h_bwd = (b && b[0] == '1') ? 1 : 0;
+    g_epi_h_bwd = (b && b[0] == '0') ? 0 : 1;
   }
   return g_epi_h == 1 && g_gemm_impl != 1;
 }
