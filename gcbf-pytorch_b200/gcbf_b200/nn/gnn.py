@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from .. import ops
+from .. import _C, ops
 from .mlp import MLP
 
 
@@ -93,6 +93,12 @@ class _GNNLayerBase(nn.Module):
         spec = self.net_spec(head)
         rowptr = cached_rowptr(edge_index, x.shape[0])
         params = MLP.flat_params(spec.all_layers())
+        if not torch.is_grad_enabled():
+            # inference (rollouts, evaluation under no_grad): nothing is saved for a backward.  (Inside Function.forward grad mode is
+            # always off and needs_input_grad ignores it, so the autograd path would keep the whole forward workspace alive per call.)
+            _C.require_cuda(x, edge_attr, edge_index)
+            fwd = ops.native_net_forward if ops.NATIVE else ops.net_forward
+            return fwd(spec, x, edge_attr, edge_index, rowptr, row_index, head_extra, False)[0]
         return ops.GNNNetFunction.apply(x, edge_attr, edge_index, rowptr, row_index, head_extra, spec, *params)
 
     def forward(self, x: Tensor, edge_attr: Tensor, edge_index: Tensor) -> Tensor:

@@ -75,5 +75,8 @@ class MLP(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         specs = self.specs()
         lead = x.shape[:-1]
-        y = ops.MLPFunction.apply(x.reshape(-1, x.shape[-1]), specs, *self.flat_params(specs))
+        if not torch.is_grad_enabled() and ops.NATIVE and len(specs) <= ops.native.MAX_LAYERS and x.is_cuda:
+            y = ops.native_mlp_forward(x.reshape(-1, x.shape[-1]), specs, False)[0]      # inference: nothing saved (see gnn.py run())
+        else:
+            y = ops.MLPFunction.apply(x.reshape(-1, x.shape[-1]), specs, *self.flat_params(specs))
         return y.reshape(*lead, y.shape[-1])

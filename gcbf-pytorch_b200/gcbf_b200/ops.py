@@ -905,7 +905,17 @@ def native_net_forward(spec, x, edge_attr, edge_index, rowptr, row_index, head_e
     out_dim = (spec.head or spec.gamma)[-1].W.shape[0]
     out = torch.empty(R, out_dim, device=dev, dtype=torch.float32)
     nbytes = native.fn('gcbf_net_forward_workspace_bytes')(ctypes.byref(nd), E, Nn, R, 1 if save else 0)
-    ws = native.workspace(nbytes, dev)
+    if save:
+        ws = native.workspace(nbytes, dev)           # lives in the autograd state until the backward has run
+    else:
+        # inference (rollouts: one actor forward per env step, a different edge count every step): a fresh torch allocation per call
+        # sends the caching allocator into cudaMalloc for every new size (measured: 10 ms steps with 80 ms stalls); one grow-only
+        # buffer per (device, stream) instead -- calls on a stream are ordered, so the next call may overwrite it
+        key = (dev.index, _C.stream())
+        gb = _INFER_WS.get(key)
+        if gb is None:
+            gb = _INFER_WS[key] = native.GrowBuffer()
+        ws = gb.get(nbytes, dev)
     nctx = native.NetCtx() if save else None
     rc = native.fn('gcbf_net_forward')(ctypes.byref(nd), ptr(xc), ptr(ea) if E else None, ptr(ei) if E else None, ptr(rowptr), E, Nn,
                                        ptr(row_index), R, ptr(he), ptr(out), out_dim, ptr(ws), ws.numel(),
@@ -914,6 +924,9 @@ def native_net_forward(spec, x, edge_attr, edge_index, rowptr, row_index, head_e
     native._mark_fresh(specs)
     state = (nctx, ws, (xc, ea, ei, rowptr, row_index, he), (E, Nn, R)) if save else None
     return out, state
+
+
+_INFER_WS = {}
 
 
 def native_net_backward(spec, state, d_out, need_d_edge_attr):
