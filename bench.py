@@ -325,6 +325,7 @@ def run_own(args):
     else:
         also = [c for c in args.also.split(',') if c and c != 'none' and c != main_cfg]
 
+    gpu_leg_threads()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     m = measure(main_cfg, args, dev, rank, world, dist, True, sampler)
     extra = {}
@@ -410,16 +411,49 @@ def run_own(args):
         dist.destroy_process_group()
 
 
+def cpu_quota():
+    """CPUs this container may use per scheduler period (cgroup v2 cpu.max, v1 cpu.cfs_quota_us), or None if unlimited.  The GPU
+    boxes of this pool report 128 logical CPUs but a quota of 16: threads beyond it only get the whole process group throttled
+    (measured: 50 ms stalls every 100 ms period in the rollout loop, /sys/fs/cgroup/cpu.stat nr_throttled)."""
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            q, p = f.read().split()[:2]
+        if q != 'max':
+            return float(q) / float(p)
+    except Exception:
+        pass
+    try:
+        with open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us') as f:
+            q = int(f.read())
+        with open('/sys/fs/cgroup/cpu/cpu.cfs_period_us') as f:
+            p = int(f.read())
+        if q > 0:
+            return q / p
+    except Exception:
+        pass
+    return None
+
+
 def host_threads():
-    """torch intra-op threads for the CPU legs: the physical cores of the box (torchrun exports OMP_NUM_THREADS=1, which
-    would pin the reference arm to a single core)."""
+    """torch intra-op threads for the CPU legs: the physical cores of the box, capped by the container's CPU quota (torchrun
+    exports OMP_NUM_THREADS=1, which would pin the reference arm to a single core)."""
     n = max(1, (os.cpu_count() or 2) // 2)
     try:
         n = min(n, len(os.sched_getaffinity(0)))
     except Exception:
         pass
+    q = cpu_quota()
+    if q:
+        n = max(1, min(n, int(q)))
     torch.set_num_threads(n)
     return torch.get_num_threads()
+
+
+def gpu_leg_threads():
+    """The GPU legs need one host thread; torch's default (one intra-op thread per logical CPU, spinning after every parallel region)
+    burns the container's CPU quota and gets the launching thread throttled with it."""
+    q = cpu_quota()
+    torch.set_num_threads(max(1, min(4, int(q) if q else 4)))
 
 
 def cpu_sample_step(cfg_name, graphs):
@@ -461,7 +495,7 @@ def cpu_baseline(cfg_name, budget_s=20.0):
     t = statistics.median(times)
     return {'value': round(graphs * sb.num_agents / t, 1), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
             'sample': f'{graphs} of {full} graphs of {cfg_name} ({sb.env} n={sb.num_agents}), median of {len(times)} steps, '
-                      f'{t:.2f} s/step; host has {os.cpu_count()} logical CPUs',
+                      f'{t:.2f} s/step; host has {os.cpu_count()} logical CPUs, container CPU quota {cpu_quota()}',
             'seconds_per_step': round(t, 3)}
 
 
@@ -493,7 +527,8 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = graphs * sb.num_agents * steps / dt
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    sample = (f'all {full} graphs per step' if graphs == full else f'{graphs} of {full} graphs per step (bounded sample)') + f', {steps} steps'
+    sample = ((f'all {full} graphs per step' if graphs == full else f'{graphs} of {full} graphs per step (bounded sample)') + f', {steps} steps'
+              + f'; host has {os.cpu_count()} logical CPUs, container CPU quota {cpu_quota()}')
     line = {'impl': 'reference', 'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': steps,
             'warmup': warmup, 'ms_per_step': round(dt / steps * 1e3, 2), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
