@@ -12,6 +12,9 @@ void set_error(const char* fmt, ...);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// in-place single-block exclusive scan of `count` int32 values, data[count] <- total (graph.cu; shared with macbf.cu)
+cudaError_t exclusive_scan_i32(int32_t* data, int count, cudaStream_t st);
+
 #define GCBF_REQUIRE(cond, ...)                 \
   do {                                          \
     if (!(cond)) {                              \

@@ -107,6 +107,11 @@ __global__ void exclusive_scan_kernel(int32_t* __restrict__ data, int count) {
   if (threadIdx.x == 0) data[count] = carry_s;
 }
 
+cudaError_t exclusive_scan_i32(int32_t* data, int count, cudaStream_t st) {
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(data, count);
+  return cudaGetLastError();
+}
+
 // rowptr[i] = first edge e with dst[e] >= i  (binary search; dst is non-decreasing)
 __global__ void rowptr_kernel(const int64_t* __restrict__ dst, int64_t E, int num_nodes, int32_t* __restrict__ rowptr,
                               int32_t* __restrict__ unsorted_flag) {

@@ -432,6 +432,47 @@ size_t gcbf_apply_workspace_bytes(const gcbf_step_desc* d, const gcbf_step_batch
 int gcbf_apply(const gcbf_step_desc* d, const gcbf_step_batch* graph, float lr, float rand, const float* noise, int max_iter,
                float* action, int ld_action, int* iterations, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * MACBF, the paper's baseline algorithm (gcbf/algo/macbf.py:20-239): the kernels it needs beyond the ones above.
+ * Its networks are small MLPs (gcbf/nn/gnn.py:82-135: per-edge CBF (8 + d_e) -> 64 -> 128 -> 64 -> 1; actor message
+ * (8 + d_e) -> 64 -> 128, MAX aggregation, 128 -> 64 -> 128 -> 64 -> a, head 2a -> 512 -> 128 -> 32 -> a) and run on
+ * gcbf_mlp_forward / gcbf_mlp_backward.
+ *
+ * Top-k filtered radius graph = `env.add_communication_links` of an env built with max_neighbors = k (train.py:30: k = 12):
+ *   metric 1 (gcbf/env/dubins_car.py:730-746, simple_drone.py:316-333): edges to the k nearest nodes that are inside the radius
+ *            (torch.topk on the distance row; equal distances: lower index first);
+ *   metric 0 (gcbf/env/simple_car.py:32-33, 249-252): torch_cluster's cap -- the first k + 1 hits in ascending source index, the
+ *            target itself included, self loop dropped.
+ * Same two-call protocol and output order (target asc, source asc) as gcbf_radius_graph_count / _fill. */
+int gcbf_radius_graph_topk_count(const float* states, int ld_state, int pos_dim, int num_graphs, int nodes_per_graph, int num_agents,
+                                 float radius, int metric, int max_neighbors, int32_t* rowptr, void* stream);
+int gcbf_radius_graph_topk_fill(const float* states, int ld_state, int pos_dim, int num_graphs, int nodes_per_graph, int num_agents,
+                                float radius, int metric, int max_neighbors, const int32_t* rowptr, int64_t* edge_index,
+                                int64_t num_edges, void* stream);
+/* env.safe_mask / unsafe_mask(data, return_edge=True) (simple_car.py:307-311, 332-336; dubins_car.py:819-823, 844-848;
+ * simple_drone.py:380-384, 405-409): dist = ||edge_attr[:, :pos_dim]||; safe = dist > 4R, unsafe = dist < 2R. */
+int gcbf_edge_masks(const float* edge_attr, int ld_edge_attr, int pos_dim, int64_t num_edges, double agent_radius, uint8_t* safe,
+                    uint8_t* unsafe, void* stream);
+/* MessagePassing(aggr='max') (gcbf/nn/gnn.py:116-119) over the CSR of a target-sorted edge list: out[i, c] = max over the
+ * incoming edges of msg[e, c], 0 for a node without incoming edges; argmax [num_nodes, channels] (edge id or -1) routes the
+ * gradient: d_msg[argmax[i, c], c] = d_out[i, c], everything else 0. */
+int gcbf_seg_max_fwd(const float* msg, int ld_msg, const int32_t* rowptr, int num_nodes, int channels, float* out, int ld_out,
+                     int32_t* argmax, void* stream);
+int gcbf_seg_max_bwd(const float* d_out, int ld_dout, const int32_t* argmax, int num_nodes, int channels, float* d_msg, int ld_dmsg,
+                     int64_t num_edges, void* stream);
+/* Losses of MACBF.update (macbf.py:140-181) over PER-EDGE h / h_next [num_edges] and per-agent actions [num_agents, action_dim], in
+ * the two passes of gcbf_loss_partials / gcbf_loss_grads (ranks may all-reduce `partial` in between).  partial: double[16] =
+ * GCBF_LP_SUM_UNSAFE .. GCBF_LP_SUM_ACT as above with GCBF_LP_CNT_ALL = num_edges, then [9] = #(h_dot + alpha h >= 0),
+ * [10] = num_agents.  scalars: float[8] = loss_unsafe, loss_safe, loss_h_dot, loss_action, acc_unsafe, acc_safe, total loss,
+ * acc_derivative. */
+int gcbf_macbf_loss_partials(const float* h, const float* h_next, const uint8_t* safe, const uint8_t* unsafe, int64_t num_edges,
+                             const float* action, int action_dim, int64_t num_agents, float alpha, float eps, float dt,
+                             double* partial, void* stream);
+int gcbf_macbf_loss_grads(const float* h, const float* h_next, const uint8_t* safe, const uint8_t* unsafe, int64_t num_edges,
+                          const float* action, int action_dim, int64_t num_agents, float alpha, float eps, float dt,
+                          float coef_unsafe, float coef_safe, float coef_hdot, float coef_action, const double* partial, float* d_h,
+                          float* d_h_next, float* d_action, float* scalars, void* stream);
+
 /* instrumentation (bench.py): kernels launched by the chain-level calls since the last reset, and optional CUDA-event timing of
  * every linear-layer launch (kind 0 forward / 1 data-grad / 2 weight-grad on the tensor cores, 3 fp32 linear kernels, 4 operand
  * preparation = amax + fp16 split) */

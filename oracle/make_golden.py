@@ -2,7 +2,8 @@
 running on oracle/shim (oracle/ref_harness.py).  Inputs are reproducible from (config, seeds) via
 gcbf_b200/synth.py and a seeded module construction, so the fixtures hold only outputs + weight digests.
 
-    python oracle/make_golden.py            # regenerate every case
+    python oracle/make_golden.py            # regenerate every GCBF case
+    python oracle/make_golden.py macbf      # regenerate the MACBF cases (tests/golden/macbf_*.pt)
 """
 import os
 import sys
@@ -20,6 +21,15 @@ CASES = {
     'dubins_n16_o4_b1_freeze': dict(env='DubinsCar', n=16, obs=4, graphs=1, area=3.0, seed=14),
     'simplecar_c1': dict(env='SimpleCar', n=16, obs=0, graphs=1, area=4.0, seed=1001),
     'simplecar_isolated': dict(env='SimpleCar', n=4, obs=0, graphs=2, area=50.0, seed=15),
+}
+# MACBF baseline: env built with max_neighbors = 12, per-edge h and masks; the nets are small, so the fixtures carry
+# the full initial state dicts (final ones as digests)
+MACBF_CASES = {
+    'macbf_dubins_n24_o6_b3': dict(env='DubinsCar', n=24, obs=6, graphs=3, area=1.6, seed=21),       # dense: the top-12 filter cuts
+    'macbf_simplecar_n20_b3': dict(env='SimpleCar', n=20, obs=0, graphs=3, area=1.2, seed=22),       # dense: torch_cluster's cap cuts
+    'macbf_drone_n10_b2': dict(env='SimpleDrone', n=10, obs=10, graphs=2, area=0.8, seed=23),
+    'macbf_dubins_sparse_b2': dict(env='DubinsCar', n=16, obs=4, graphs=2, area=6.0, seed=24),       # nodes without incoming edges
+    'macbf_dubins_single': dict(env='DubinsCar', n=16, obs=4, graphs=1, area=2.0, seed=25),          # one graph: reach-freeze branch
 }
 INIT_SEED = 0
 STEPS = 2
@@ -57,5 +67,29 @@ def main():
               f'safe={int(res["safe_mask"].sum())} loss_hdot={s["loss/derivative"]:.6f} -> {os.path.getsize(path)} B')
 
 
+def main_macbf():
+    synth = ref_harness._load_synth()
+    out_dir = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+    for name, c in MACBF_CASES.items():
+        sb = synth.make_states(c['env'], c['n'], c['obs'], c['graphs'], c['area'], c['seed'])
+        if name.endswith('single'):
+            sb.states[0, :2] = sb.goals[0, :2]
+        res = ref_harness.run_reference(sb, INIT_SEED, None, STEPS, algo_name='macbf')
+        fix = dict(meta=dict(c, init_seed=INIT_SEED, steps=STEPS, num_obs=sb.num_obs, case=name, algo='macbf', max_neighbors=12),
+                   states=sb.states, goals=sb.goals, **{k: res[k] for k in (
+                       'edge_index', 'u_ref', 'edge_attr', 'h_probe', 'u_probe', 'unsafe_mask', 'safe_mask', 'states_next_probe',
+                       'apply_action', 'steps', 'cbf_init', 'actor_init')},
+                   cbf_final=digest(res['cbf_final']), actor_final=digest(res['actor_final']))
+        path = os.path.join(out_dir, name + '.pt')
+        torch.save(fix, path)
+        s = res['steps'][-1]['scalars']
+        deg = torch.bincount(res['edge_index'][1]).max() if res['edge_index'].numel() else 0
+        print(f'{name}: E={res["edge_index"].shape[1]} max in-degree={int(deg)} unsafe={int(res["unsafe_mask"].sum())} '
+              f'safe={int(res["safe_mask"].sum())} loss_hdot={s["loss/derivative"]:.6f} -> {os.path.getsize(path)} B')
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'macbf':
+        main_macbf()
+    else:
+        main()

@@ -38,7 +38,7 @@ class DictWriter:
         self.scalars[tag] = float(value)
 
 
-def build_reference(sb, init_seed=0, pretrained=None, hyperparams=None):
+def build_reference(sb, init_seed=0, pretrained=None, hyperparams=None, algo_name='gcbf'):
     """Returns (env, algo, graph_list) with the synthetic state injected into the reference env."""
     sys.path.insert(0, HERE)
     from ref_loader import load_reference
@@ -54,7 +54,8 @@ def build_reference(sb, init_seed=0, pretrained=None, hyperparams=None):
     params = env.default_params
     params['area_size'] = sb.area_size
     params['num_obs'] = sb.num_obs
-    env = make_env(sb.env, sb.num_agents, dev, params=params)
+    max_nb = 12 if algo_name == 'macbf' else None          # train.py:30
+    env = make_env(sb.env, sb.num_agents, dev, params=params, max_neighbors=max_nb)
     env.train()
     env._goal = sb.goals.clone()
     if sb.env != 'SimpleCar':
@@ -73,15 +74,16 @@ def build_reference(sb, init_seed=0, pretrained=None, hyperparams=None):
         d.update(Data(u_ref=env.u_ref(d)))
         graphs.append(d)
     torch.manual_seed(init_seed)
-    hp = read_params(sb.env, 'gcbf') if hyperparams is None else hyperparams
-    algo = make_algo('gcbf', env, n, env.node_dim, env.edge_dim, env.action_dim, dev, 512, hp)
+    hp = read_params(sb.env, algo_name) if hyperparams is None else hyperparams
+    algo = make_algo(algo_name, env, n, env.node_dim, env.edge_dim, env.action_dim, dev, 512, hp)
     if pretrained is not None:
         algo.load(pretrained)
     return env, algo, graphs
 
 
-def run_reference(sb, init_seed=0, pretrained=None, n_steps=1):
-    env, algo, graphs = build_reference(sb, init_seed, pretrained)
+def run_reference(sb, init_seed=0, pretrained=None, n_steps=1, algo_name='gcbf'):
+    env, algo, graphs = build_reference(sb, init_seed, pretrained, algo_name=algo_name)
+    edge = algo_name == 'macbf'                      # MACBF: per-edge h and per-edge masks
     from torch_geometric.data import Batch
     out = {}
     out['cbf_init'] = {k: v.clone() for k, v in algo.cbf.state_dict().items()}
@@ -96,8 +98,8 @@ def run_reference(sb, init_seed=0, pretrained=None, n_steps=1):
     with torch.no_grad():
         out['h_probe'] = cbf_c(batch).clone()
         out['u_probe'] = actor_c(batch).clone()
-        out['unsafe_mask'] = env.unsafe_mask(batch).clone()
-        out['safe_mask'] = env.safe_mask(batch).clone()
+        out['unsafe_mask'] = env.unsafe_mask(batch, return_edge=edge).clone()
+        out['safe_mask'] = env.safe_mask(batch, return_edge=edge).clone()
         nxt = env.forward_graph(batch, out['u_probe'])
         out['states_next_probe'] = nxt.states.clone()
     # --- test-time controller on the first graph (noise off: rand=0) ---------------------------------
@@ -131,13 +133,14 @@ def main():
     ap.add_argument('--init-seed', type=int, default=0)
     ap.add_argument('--pretrained', default=None)
     ap.add_argument('--steps', type=int, default=1)
+    ap.add_argument('--algo', default='gcbf', choices=['gcbf', 'macbf'])
     ap.add_argument('--out', required=True)
     a = ap.parse_args()
     synth = _load_synth()
     sb = synth.make_states(a.env, a.n, a.obs, a.graphs, a.area, a.seed)
-    res = run_reference(sb, a.init_seed, a.pretrained, a.steps)
+    res = run_reference(sb, a.init_seed, a.pretrained, a.steps, a.algo)
     res['meta'] = dict(env=a.env, n=a.n, obs=sb.num_obs, graphs=a.graphs, area=a.area, seed=a.seed,
-                       init_seed=a.init_seed, pretrained=a.pretrained, steps=a.steps)
+                       init_seed=a.init_seed, pretrained=a.pretrained, steps=a.steps, algo=a.algo)
     res['states'] = sb.states
     res['goals'] = sb.goals
     torch.save(res, a.out)

@@ -26,7 +26,11 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_cases():
-    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and not f.startswith('pretrained'))
+    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and not f.startswith(('pretrained', 'macbf_')))
+
+
+def macbf_golden_cases():
+    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith('.pt') and f.startswith('macbf_'))
 
 
 def load_golden(name):

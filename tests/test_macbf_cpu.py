@@ -1,0 +1,216 @@
+"""CPU tests of the MACBF path:
+  1. the port (oracle/macbf_oracle.py) against the golden fixtures generated from the reference-on-shim (oracle/make_golden.py macbf);
+  2. the host build of the per-element functions the CUDA kernels are made of (csrc/macbf_core.h via tests/host_driver/macbf_host.cpp,
+     compiled here with g++ -ffp-contract=off) against the fixtures / the port: top-k radius graph bit-exact, per-edge masks equal,
+     max aggregation forward + backward against torch, losses and their gradients against autograd;
+  3. the product-side host logic that needs no GPU (factories, state-dict keys, seeded initialisation, the reference's no-op apply).
+"""
+import copy
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import gcbf_oracle as O
+import macbf_oracle as MO
+from conftest import ROOT, digest_close, load_golden, macbf_golden_cases
+from helpers import case_inputs
+
+CASES = macbf_golden_cases()
+
+
+def _inputs(fix):
+    meta = fix['meta']
+    sb = case_inputs(meta)
+    if meta['case'].endswith('single'):
+        sb.states[0, :2] = sb.goals[0, :2]
+    assert torch.equal(sb.states, fix['states']) and torch.equal(sb.goals, fix['goals'])
+    return meta, sb
+
+
+@pytest.fixture(scope='module')
+def host():
+    """tests/host_driver/macbf_host.cpp -> shared object (the kernels' arithmetic, serial)."""
+    out = os.path.join(ROOT, 'tests', 'host_driver', '_build')
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, 'macbf_host.so')
+    src = os.path.join(ROOT, 'tests', 'host_driver', 'macbf_host.cpp')
+    subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-I', os.path.join(ROOT, 'gcbf-pytorch_b200', 'csrc'),
+                           '-o', so, src])
+    lib = ctypes.CDLL(so)
+    lib.host_radius_graph_topk.restype = ctypes.c_int64
+    return lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def host_topk(lib, env, states, B, N, n, k):
+    p = O.ENV_PARAMS[env]
+    st = states.contiguous()
+    rowptr = torch.zeros(B * n + 1, dtype=torch.int32)
+    args = (_p(st), ctypes.c_int(st.shape[1]), ctypes.c_int(p['pos_dim']), ctypes.c_int(B), ctypes.c_int(N), ctypes.c_int(n),
+            ctypes.c_float(p['comm_radius']), ctypes.c_int(0 if env == 'SimpleCar' else 1), ctypes.c_int(k), _p(rowptr))
+    E = lib.host_radius_graph_topk(*args, None, ctypes.c_int64(0))
+    ei = torch.zeros(2, E, dtype=torch.int64)
+    lib.host_radius_graph_topk(*args, _p(ei), ctypes.c_int64(E))
+    return ei, rowptr
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_port_matches_golden(case):
+    fix = load_golden(case)
+    meta, sb = _inputs(fix)
+    env, n, o, B = sb.env, sb.num_agents, sb.num_obs, sb.num_graphs
+    N = n + o
+    ei = MO.batch_radius_graph_topk(env, sb.states, B, N, n)
+    assert torch.equal(ei, fix['edge_index'])
+    K = O.lqr_gain(env) if env != 'DubinsCar' else None
+    x, am = O.make_graph_inputs(env, sb.states, B, n, o)
+    ur = O.u_ref(env, sb.states if am is None else sb.states[am], sb.goals, K)
+    assert torch.allclose(ur, fix['u_ref'], rtol=0, atol=1e-6)      # (the LQR matmul rounds differently per batch shape)
+    ur = fix['u_ref']
+    e_attr = O.edge_attr(env, sb.states, ei)
+    assert torch.equal(e_attr, fix['edge_attr'])
+    cbf, act = copy.deepcopy(fix['cbf_init']), copy.deepcopy(fix['actor_init'])
+    with torch.no_grad():
+        h = MO.cbf_net_forward(cbf, x, e_attr, ei)
+        u = MO.controller_forward(act, x, e_attr, ei, am, ur)
+    assert torch.allclose(h, fix['h_probe'], rtol=0, atol=1e-7) and torch.allclose(u, fix['u_probe'], rtol=0, atol=1e-7)
+    sm, um = MO.edge_masks(env, e_attr)
+    assert torch.equal(sm, fix['safe_mask']) and torch.equal(um, fix['unsafe_mask'])
+    # MACBF.apply of the reference never moves the action (its leaf does not require grad): it returns the actor's output
+    ei0 = ei[:, ei[1] < N]
+    a0 = MO.apply_controller(env, cbf, act, sb.states[:N], sb.goals, ei0, ur[:n], n, o)
+    assert torch.allclose(a0, fix['apply_action'], rtol=0, atol=1e-7)
+    assert torch.equal(fix['apply_action'], fix['u_probe'][:n]) or torch.allclose(fix['apply_action'], fix['u_probe'][:n], atol=1e-6)
+    oc, oa = {}, {}
+    for gold in fix['steps']:
+        st = MO.update_step(env, cbf, act, oc, oa, sb.states, sb.goals, ei, ur, B, n, o, K=K)
+        for tag, key in (('loss/unsafe', 'loss_unsafe'), ('loss/safe', 'loss_safe'), ('loss/derivative', 'loss_h_dot'),
+                         ('loss/action', 'loss_action'), ('acc/unsafe', 'acc_unsafe'), ('acc/safe', 'acc_safe'),
+                         ('acc/derivative', 'acc_h_dot')):
+            assert abs(float(st[key]) - gold['scalars'][tag]) <= 1e-6, (tag, float(st[key]), gold['scalars'][tag])
+    assert not digest_close(cbf, fix['cbf_final'], 1e-6, 1e-6)
+    assert not digest_close(act, fix['actor_final'], 1e-6, 1e-6)
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_kernel_arithmetic_topk_and_edge_masks_bit_exact(host, case):
+    fix = load_golden(case)
+    meta, sb = _inputs(fix)
+    env, n, o, B = sb.env, sb.num_agents, sb.num_obs, sb.num_graphs
+    ei, rowptr = host_topk(host, env, sb.states, B, n + o, n, 12)
+    assert torch.equal(ei, fix['edge_index'])
+    assert int(rowptr[-1]) == ei.shape[1]
+    ea = fix['edge_attr'].contiguous()
+    E = ea.shape[0]
+    safe, unsafe = torch.zeros(E, dtype=torch.uint8), torch.zeros(E, dtype=torch.uint8)
+    host.host_edge_masks(_p(ea), ctypes.c_int(ea.shape[1]), ctypes.c_int(O.ENV_PARAMS[env]['pos_dim']), ctypes.c_int64(E),
+                         ctypes.c_double(O.ENV_PARAMS[env]['radius']), _p(safe), _p(unsafe))
+    assert torch.equal(safe.bool(), fix['safe_mask']) and torch.equal(unsafe.bool(), fix['unsafe_mask'])
+
+
+@pytest.mark.parametrize('env,n,o,B,area,k', [('DubinsCar', 40, 10, 4, 1.2, 12), ('SimpleDrone', 30, 30, 3, 0.7, 12), ('SimpleCar', 50, 0, 3, 1.0, 12),
+                                               ('DubinsCar', 16, 0, 2, 1.0, 3), ('SimpleCar', 9, 0, 2, 0.5, 2), ('SimpleDrone', 14, 14, 1, 5.0, 12)])
+def test_kernel_arithmetic_topk_dense_random(host, env, n, o, B, area, k):
+    """Very dense graphs (every agent has far more than k nodes in range) and tiny k against the port's torch.topk / cumsum."""
+    from gcbf_b200 import synth
+    sb = synth.make_states(env, n, o, B, area, 77)
+    N = sb.nodes_per_graph
+    want = MO.batch_radius_graph_topk(env, sb.states, B, N, n, k)
+    got, _ = host_topk(host, env, sb.states, B, N, n, k)
+    assert torch.equal(got, want)
+    if k < N - 1 and area < 2:
+        assert int(torch.bincount(want[1]).max()) >= k      # the filter is active in the dense cases
+
+
+def test_kernel_arithmetic_edge_norm_matches_torch_on_strided_rows(host):
+    """||edge_attr[:, :pos_dim]|| feeds two threshold tests: the fma-chain formula of macbf_core.h against torch.norm on the strided
+    slice the reference takes, on 2e5 random rows and on rows placed within a few ulps of both thresholds."""
+    g = torch.Generator().manual_seed(3)
+    for env in ('SimpleCar', 'DubinsCar', 'SimpleDrone'):
+        p = O.ENV_PARAMS[env]
+        pd, R = p['pos_dim'], p['radius']
+        ea = (torch.rand(200_000, p['edge_dim'], generator=g) - 0.5) * 0.6
+        # rows scaled onto the thresholds, then nudged by a few ulps
+        for thr in (4 * R, 2 * R):
+            blk = ea[:20_000, :pd]
+            blk *= (thr / blk.norm(dim=-1, keepdim=True))
+            blk *= 1 + (torch.randint(-3, 4, (20_000, 1), generator=g).float() * 6e-8)
+            ea = torch.cat([ea, torch.cat([blk, torch.zeros(20_000, p['edge_dim'] - pd)], dim=1)], dim=0)
+        ea = ea.contiguous()
+        E = ea.shape[0]
+        safe, unsafe = torch.zeros(E, dtype=torch.uint8), torch.zeros(E, dtype=torch.uint8)
+        host.host_edge_masks(_p(ea), ctypes.c_int(ea.shape[1]), ctypes.c_int(pd), ctypes.c_int64(E), ctypes.c_double(R), _p(safe), _p(unsafe))
+        sm, um = MO.edge_masks(env, ea)
+        assert int((safe.bool() != sm).sum()) == 0 and int((unsafe.bool() != um).sum()) == 0, env
+
+
+@pytest.mark.parametrize('C,deg_hi', [(128, 13), (5, 40), (1, 3)])
+def test_kernel_arithmetic_seg_max(host, C, deg_hi):
+    g = torch.Generator().manual_seed(C)
+    Nn = 57
+    deg = torch.randint(0, deg_hi + 1, (Nn,), generator=g)
+    deg[3] = 0
+    deg[Nn - 1] = 0
+    dst = torch.repeat_interleave(torch.arange(Nn), deg)
+    E = int(deg.sum())
+    rowptr = torch.zeros(Nn + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(deg, 0).int()
+    ld = C + 3
+    buf = torch.randn(E, ld, generator=g)
+    msg = buf[:, :C]
+    out, arg = torch.full((Nn, C), 7.0), torch.zeros(Nn, C, dtype=torch.int32)
+    host.host_seg_max_fwd(_p(buf), ctypes.c_int(ld), _p(rowptr), ctypes.c_int(Nn), ctypes.c_int(C), _p(out), ctypes.c_int(C), _p(arg))
+    m = msg.clone().requires_grad_(True)
+    want = torch.zeros(Nn, C).scatter_reduce(0, dst.view(-1, 1).expand(E, C), m, reduce='amax', include_self=False)
+    assert torch.equal(out, want.detach())
+    assert bool((arg[deg == 0] == -1).all()) and bool((out[deg == 0] == 0).all())
+    d_out = torch.randn(Nn, C, generator=g)
+    want.backward(d_out)
+    d_msg = torch.full((E, C), 3.0)
+    host.host_seg_max_bwd(_p(d_out), ctypes.c_int(C), _p(arg), ctypes.c_int(Nn), ctypes.c_int(C), _p(d_msg), ctypes.c_int(C), ctypes.c_int64(E))
+    assert torch.equal(d_msg, m.grad)          # no ties in random floats: one winner per cell
+
+
+@pytest.mark.parametrize('E,M,ad,empty', [(500, 60, 2, None), (64, 10, 3, 'unsafe'), (33, 7, 2, 'safe'), (1, 1, 2, None)])
+def test_kernel_arithmetic_losses_match_autograd(host, E, M, ad, empty):
+    g = torch.Generator().manual_seed(E)
+    h = (torch.randn(E, generator=g) * 0.05).requires_grad_(True)
+    hn = (h.detach() + torch.randn(E, generator=g) * 0.002).requires_grad_(True)
+    act = torch.randn(M, ad, generator=g).requires_grad_(True)
+    safe = torch.rand(E, generator=g) < 0.6
+    unsafe = (torch.rand(E, generator=g) < 0.2) & ~safe
+    if empty == 'unsafe':
+        unsafe[:] = False
+    if empty == 'safe':
+        safe[:] = False
+    alpha, eps, dt, cu, cs, ch, ca = 1.0, 0.02, 0.03, 1.0, 0.7, 0.4, 0.05
+    # macbf.py:140-177
+    hu, hs = h[unsafe], h[safe]
+    lu = torch.relu(hu + eps).mean() if hu.numel() else torch.tensor(0.0)
+    ls = torch.relu(-hs + eps).mean() if hs.numel() else torch.tensor(0.0)
+    h_dot = (hn - h) / dt
+    lh = torch.relu(-h_dot - alpha * h + eps).mean()
+    la = torch.square(act).sum(dim=1).mean()
+    loss = cu * lu + cs * ls + ch * lh + ca * la
+    loss.backward()
+    acc = [(hu < 0).float().mean() if hu.numel() else 1.0, (hs >= 0).float().mean() if hs.numel() else 1.0, ((h_dot + alpha * h) >= 0).float().mean()]
+    partial = torch.zeros(16, dtype=torch.float64)
+    d_h, d_hn, d_act, sc = torch.zeros(E), torch.zeros(E), torch.zeros(M, ad), torch.zeros(8)
+    hd, hnd, ad_ = h.detach().contiguous(), hn.detach().contiguous(), act.detach().contiguous()
+    s8, u8 = safe.to(torch.uint8), unsafe.to(torch.uint8)
+    f = ctypes.c_float
+    host.host_macbf_loss(_p(hd), _p(hnd), _p(s8), _p(u8), ctypes.c_int64(E), _p(ad_), ctypes.c_int(ad), ctypes.c_int64(M), f(alpha), f(eps), f(dt),
+                         f(cu), f(cs), f(ch), f(ca), _p(partial), _p(d_h), _p(d_hn), _p(d_act), _p(sc))
+    for got, want in zip(sc.tolist(), [lu, ls, lh, la, acc[0], acc[1], loss, acc[2]]):
+        assert abs(got - float(want)) <= 1e-6
+    assert torch.allclose(d_h, h.grad, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(d_hn, hn.grad, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(d_act, act.grad, rtol=1e-6, atol=1e-9)
+    assert partial[7] == E and partial[10] == M
