@@ -15,7 +15,8 @@ for _name in ('nn', 'controller', 'algo', 'env', 'trainer', 'data'):
     _mod = importlib.import_module(f'gcbf_b200.{_name}')
     sys.modules[f'gcbf.{_name}'] = _mod
     globals()[_name] = _mod
-for _sub in ('nn.mlp', 'nn.gnn', 'nn.utils', 'controller.gnn_controller', 'controller.base', 'algo.gcbf', 'algo.base',
+for _sub in ('nn.mlp', 'nn.gnn', 'nn.utils', 'controller.gnn_controller', 'controller.macbf_controller', 'controller.nominal', 'controller.base', 'algo.gcbf', 'algo.macbf',
+             'algo.nominal', 'algo.base',
              'algo.buffer', 'env.base', 'env.simple_car', 'env.dubins_car', 'env.simple_drone', 'trainer.trainer',
              'trainer.utils'):
     sys.modules[f'gcbf.{_sub}'] = importlib.import_module(f'gcbf_b200.{_sub}')

@@ -78,6 +78,15 @@ _SIGS = {
     'gcbf_sn_grad_fixup': (c_int, [P, c_int, P, c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
     'gcbf_grad_sumsq': (c_int, [P, c_int64, P, P]),
     'gcbf_clip_adam': (c_int, [P, P, P, P, c_int64, P, c_double, c_double, c_double, c_double, c_double, c_int, P]),
+    # MACBF baseline (csrc/macbf.cu)
+    'gcbf_radius_graph_topk_count': (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P, P]),
+    'gcbf_radius_graph_topk_fill': (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, P, P, c_int64, P]),
+    'gcbf_edge_masks': (c_int, [P, c_int, c_int, c_int64, c_double, P, P, P]),
+    'gcbf_seg_max_fwd': (c_int, [P, c_int, P, c_int, c_int, P, c_int, P, P]),
+    'gcbf_seg_max_bwd': (c_int, [P, c_int, P, c_int, c_int, P, c_int, c_int64, P]),
+    'gcbf_macbf_loss_partials': (c_int, [P, P, P, P, c_int64, P, c_int, c_int64, c_float, c_float, c_float, P, P]),
+    'gcbf_macbf_loss_grads': (c_int, [P, P, P, P, c_int64, P, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_float,
+                                      c_float, P, P, P, P, P, P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
@@ -139,7 +148,7 @@ def check(rc, what):
 
 
 # kernels launched by one call of each entry point (for bench.py's `gpu_launches`; memsets are not counted)
-_KERNELS_PER_CALL = {'gcbf_radius_graph_count': 2, 'gcbf_sn_power_iter': 4, 'gcbf_sn_power_iter_batched': 4, 'gcbf_sn_grad_fixup': 2, 'gcbf_linear_bwd_weight': 2,
+_KERNELS_PER_CALL = {'gcbf_radius_graph_count': 2, 'gcbf_radius_graph_topk_count': 2, 'gcbf_sn_power_iter': 4, 'gcbf_sn_power_iter_batched': 4, 'gcbf_sn_grad_fixup': 2, 'gcbf_linear_bwd_weight': 2,
                      'gcbf_linear_h_supported': 0, 'gcbf_amax_split_batched': 2}
 KERNEL_LAUNCHES = 0
 ABI_CALLS = 0

@@ -93,10 +93,7 @@ class GCBF(Algorithm):
                  batch_size: int = 500, params: Optional[dict] = None):
         super().__init__(env=env, num_agents=num_agents, node_dim=node_dim, edge_dim=edge_dim, action_dim=action_dim,
                          device=device)
-        # models: same construction order as the reference (gcbf.py:87-100) => same seeded initialisation
-        self.cbf = CBFGNN(num_agents=num_agents, node_dim=node_dim, edge_dim=edge_dim, phi_dim=256).to(device)
-        self.actor = GNNController(num_agents=num_agents, node_dim=node_dim, edge_dim=edge_dim, phi_dim=256,
-                                   action_dim=action_dim).to(device)
+        self._build_networks(num_agents, node_dim, edge_dim, action_dim, device)
         self.lr_cbf, self.lr_actor = 3e-4, 1e-3            # gcbf.py:102-103
         self.max_grad_norm = 1e-3                          # gcbf.py:223-224
         self._bucket: Optional[_FlatBucket] = None
@@ -108,6 +105,12 @@ class GCBF(Algorithm):
             'alpha': 1.0, 'eps': 0.02, 'inner_iter': 10, 'loss_action_coef': 0.001, 'loss_unsafe_coef': 1.,
             'loss_safe_coef': 1., 'loss_h_dot_coef': 0.1}
         self.process_group = None   # set to a torch.distributed group for data-parallel training
+
+    def _build_networks(self, num_agents: int, node_dim: int, edge_dim: int, action_dim: int, device):
+        # models: same construction order as the reference (gcbf.py:87-100) => same seeded initialisation
+        self.cbf = CBFGNN(num_agents=num_agents, node_dim=node_dim, edge_dim=edge_dim, phi_dim=256).to(device)
+        self.actor = GNNController(num_agents=num_agents, node_dim=node_dim, edge_dim=edge_dim, phi_dim=256,
+                                   action_dim=action_dim).to(device)
 
     # ---- rollout-time API ---------------------------------------------------------------------------
     @torch.no_grad()

@@ -67,10 +67,11 @@ class MultiAgentEnv(ABC):
         self._device = device
         self._dt = dt
         self._params = self.default_params if params is None else params
-        if max_neighbors is not None:
-            raise NotImplementedError('max_neighbors (top-k neighbour filter) is only used by the MACBF baseline, '
-                                      'which is outside the hot path this package implements')
-        self._max_neighbors = None
+        if max_neighbors is not None and int(max_neighbors) < 1:
+            raise ValueError(f'max_neighbors must be >= 1, got {max_neighbors}')
+        # top-k neighbour filter of the MACBF baseline (train.py:30 builds the env with max_neighbors = 12): switches
+        # add_communication_links to the filtered radius-graph kernel (csrc/macbf.cu)
+        self._max_neighbors = None if max_neighbors is None else int(max_neighbors)
         self._data = None
         self._goal = None
         self._K = None
@@ -160,8 +161,12 @@ class MultiAgentEnv(ABC):
     def add_communication_links(self, data):
         """Radius graph + edge features (K1 + K2) for a single graph or a whole batch in one launch."""
         B = self._num_graphs_of(data)
-        ei, _ = ops.radius_graph(data.states.detach(), self.POS_DIM, B, self.nodes_per_graph, self._num_agents,
-                                 self._params['comm_radius'], self.GRAPH_METRIC)
+        if self._max_neighbors is not None:
+            ei, _ = ops.radius_graph_topk(data.states.detach(), self.POS_DIM, B, self.nodes_per_graph, self._num_agents,
+                                          self._params['comm_radius'], self.GRAPH_METRIC, self._max_neighbors)
+        else:
+            ei, _ = ops.radius_graph(data.states.detach(), self.POS_DIM, B, self.nodes_per_graph, self._num_agents,
+                                     self._params['comm_radius'], self.GRAPH_METRIC)
         data.update(Data(edge_index=ei, edge_attr=self.edge_attr(data.states, ei)))
         from ..nn.gnn import prime_rowptr
         prime_rowptr(ei, int(data.states.shape[0]))      # the CSR the GNN passes need: known sorted, no check / host sync later
@@ -210,14 +215,19 @@ class MultiAgentEnv(ABC):
         _C.call('gcbf_masks', ctypes.byref(cfg), _C.ptr(st), ld, _C.ptr(out[0]), _C.ptr(out[1]), _C.ptr(out[2]))
         return out.view(torch.bool)
 
+    def edge_masks(self, data) -> Tensor:
+        """[2, E] bool: (safe, unsafe) per edge = the `return_edge=True` branches of safe_mask / unsafe_mask (simple_car.py:307-311,
+        332-336 and siblings): dist = ||edge_attr[:, :pos_dim]||, safe = dist > 4R, unsafe = dist < 2R.  One launch for both."""
+        return ops.edge_masks(data.edge_attr, self.POS_DIM, float(self._params[self.RADIUS_KEY]))
+
     def safe_mask(self, data, return_edge: bool = False) -> Tensor:
         if return_edge:
-            raise NotImplementedError('return_edge masks are MACBF-only (outside the hot path)')
+            return self.edge_masks(data)[0]
         return self._masks(data)[0]
 
     def unsafe_mask(self, data, return_edge: bool = False) -> Tensor:
         if return_edge:
-            raise NotImplementedError('return_edge masks are MACBF-only (outside the hot path)')
+            return self.edge_masks(data)[1]
         return self._masks(data)[1]
 
     def collision_mask(self, data) -> Tensor:

@@ -1,2 +1,2 @@
 from .mlp import MLP
-from .gnn import ControllerGNNLayer, CBFGNNLayer, AttentionalAggregation, GraphSequential
+from .gnn import ControllerGNNLayer, CBFGNNLayer, CBFNetLayer, MACBFControllerLayer, AttentionalAggregation, GraphSequential

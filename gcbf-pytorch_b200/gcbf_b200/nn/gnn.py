@@ -131,3 +131,33 @@ class CBFGNNLayer(_GNNLayerBase):
 class ControllerGNNLayer(_GNNLayerBase):
     """reference gnn.py:56-73."""
     limit_lip = False
+
+
+# ---- MACBF baseline layers (reference gcbf/nn/gnn.py:82-135; SURVEY 8f-4) -------------------------------------------------------
+class CBFNetLayer(nn.Module):
+    """Per-EDGE CBF value h_ij = phi(cat[x_i, x_j, e_ij]) -- `propagate` without aggregation (reference gnn.py:82-113).  The MLP
+    (widths 64 / 128 / 64) runs on the linear kernels of the narrow ends of the GCBF MLPs (csrc/net.cu `mlp_forward` dispatch)."""
+
+    def __init__(self, node_dim: int, edge_dim: int, output_dim: int):
+        super().__init__()
+        self.phi = MLP(in_channels=2 * node_dim + edge_dim, out_channels=output_dim, hidden_layers=(64, 128, 64), limit_lip=False)
+
+    def forward(self, x: Tensor, edge_attr: Tensor, edge_index: Tensor) -> Tensor:
+        return self.phi(ops.EdgeInputFunction.apply(x, edge_attr, edge_index))
+
+
+class MACBFControllerLayer(nn.Module):
+    """m_ij = phi(cat[x_i, x_j, e_ij]); aggr_i = max_j m_ij (0 without incoming edges); out_i = gamma(aggr_i) -- reference
+    gnn.py:116-135 (`MessagePassing(aggr='max')`).  The maximum is a CSR kernel over the target-sorted edge list that also records
+    the arg-max edge of every (node, channel) for the backward (csrc/macbf.cu)."""
+
+    def __init__(self, node_dim: int, edge_dim: int, output_dim: int, phi_dim: int):
+        super().__init__()
+        self.phi = MLP(in_channels=2 * node_dim + edge_dim, out_channels=phi_dim, hidden_layers=(64,))
+        self.gamma = MLP(in_channels=phi_dim, out_channels=output_dim, hidden_layers=(64, 128, 64))
+
+    def forward(self, x: Tensor, edge_attr: Tensor, edge_index: Tensor) -> Tensor:
+        msg = self.phi(ops.EdgeInputFunction.apply(x, edge_attr, edge_index))
+        num_nodes = int(x.shape[0])
+        aggr = ops.SegMaxFunction.apply(msg, cached_rowptr(edge_index, num_nodes), num_nodes)
+        return self.gamma(aggr)

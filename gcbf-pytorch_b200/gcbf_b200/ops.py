@@ -499,6 +499,125 @@ def radius_graph(states: torch.Tensor, pos_dim: int, num_graphs: int, nodes_per_
     return ei, rowptr
 
 
+def radius_graph_topk(states: torch.Tensor, pos_dim: int, num_graphs: int, nodes_per_graph: int, num_agents: int,
+                      radius: float, metric: int, max_neighbors: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1 with the top-k neighbour filter of an env built with `max_neighbors` (MACBF; reference dubins_car.py:736-740,
+    simple_drone.py:322-326, simple_car.py:32-33): same protocol and output order as radius_graph."""
+    _C.require_cuda(states)
+    st, ld = _mat(states)
+    na = num_graphs * num_agents
+    rowptr = torch.empty(na + 1, device=st.device, dtype=torch.int32)
+    call('gcbf_radius_graph_topk_count', ptr(st), ld, pos_dim, num_graphs, nodes_per_graph, num_agents, float(radius), metric,
+         int(max_neighbors), ptr(rowptr))
+    E = int(rowptr[-1].item())
+    ei = torch.empty(2, E, device=st.device, dtype=torch.int64)
+    call('gcbf_radius_graph_topk_fill', ptr(st), ld, pos_dim, num_graphs, nodes_per_graph, num_agents, float(radius), metric,
+         int(max_neighbors), ptr(rowptr), ptr(ei) if E else None, E)
+    return ei, rowptr
+
+
+def edge_masks(edge_attr: torch.Tensor, pos_dim: int, agent_radius: float) -> torch.Tensor:
+    """(safe, unsafe) per EDGE as a [2, E] bool tensor: env.safe_mask / unsafe_mask(data, return_edge=True)."""
+    _C.require_cuda(edge_attr)
+    ea, ld = _mat(edge_attr.detach())
+    E = int(ea.shape[0])
+    out = torch.empty(2, E, device=ea.device, dtype=torch.uint8)
+    call('gcbf_edge_masks', ptr(ea) if E else None, ld, pos_dim, E, float(agent_radius), ptr(out[0]) if E else None,
+         ptr(out[1]) if E else None)
+    return out.view(torch.bool)
+
+
+class EdgeInputFunction(torch.autograd.Function):
+    """cat[x_i, x_j, e_ij] per edge (the `message` input of every layer in gcbf/nn/gnn.py); x is the node-type indicator and
+    carries no gradient, d edge_attr is the last `edge_dim` columns of the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, x, edge_attr, edge_index):
+        _C.require_cuda(x, edge_attr, edge_index)
+        xc, ea, ei = x.detach().contiguous(), edge_attr.detach().contiguous(), edge_index.contiguous()
+        E, nd, ed = int(ei.shape[1]), int(xc.shape[1]), int(ea.shape[1])
+        out = torch.empty(E, 2 * nd + ed, device=xc.device, dtype=torch.float32)
+        call('gcbf_edge_input_fwd', ptr(xc), nd, ptr(ea) if E else None, ed, ptr(ei) if E else None, E, ptr(out) if E else None,
+             2 * nd + ed)
+        ctx.dims = (nd, ed)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        nd, ed = ctx.dims
+        d_ea = None
+        if ctx.needs_input_grad[1]:
+            E = int(d_out.shape[0])
+            d_ea = torch.empty(E, ed, device=d_out.device, dtype=torch.float32)
+            if E:
+                copy2d(d_out[:, 2 * nd:], d_ea, E, ed)
+        return None, d_ea, None
+
+
+class SegMaxFunction(torch.autograd.Function):
+    """MessagePassing(aggr='max') (gcbf/nn/gnn.py:116-119): per-target maximum of the incoming messages over the CSR of the
+    target-sorted edge list, 0 for nodes without incoming edges; the gradient goes to the arg-max edge of every (node, channel)."""
+
+    @staticmethod
+    def forward(ctx, msg, rowptr, num_nodes):
+        _C.require_cuda(msg, rowptr)
+        m, ld = _mat(msg.detach())
+        E, C = int(m.shape[0]), int(m.shape[1])
+        out = torch.empty(num_nodes, C, device=m.device, dtype=torch.float32)
+        arg = torch.empty(num_nodes, C, device=m.device, dtype=torch.int32)
+        call('gcbf_seg_max_fwd', ptr(m) if E else None, ld, ptr(rowptr), num_nodes, C, ptr(out), C, ptr(arg))
+        ctx.save_for_backward(arg)
+        ctx.dims = (E, C, num_nodes)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (arg,) = ctx.saved_tensors
+        E, C, num_nodes = ctx.dims
+        d, ld = _mat(d_out)
+        d_msg = torch.empty(E, C, device=d_out.device, dtype=torch.float32)
+        call('gcbf_seg_max_bwd', ptr(d), ld, ptr(arg), num_nodes, C, ptr(d_msg) if E else None, C, E)
+        return d_msg, None, None
+
+
+class GatherCatFunction(torch.autograd.Function):
+    """cat([feat[agent_mask], extra], dim=1) (gcbf/controller/macbf_controller.py:44-46): row gather (identity when row_index is
+    None) + column concatenation in one output buffer; backward scatters the feature columns back to the selected rows."""
+
+    @staticmethod
+    def forward(ctx, feat, row_index, extra):
+        _C.require_cuda(feat, extra)
+        f = feat.detach()
+        R = int(row_index.numel()) if row_index is not None else int(f.shape[0])
+        F, X = int(f.shape[1]), int(extra.shape[1])
+        out = torch.empty(R, F + X, device=f.device, dtype=torch.float32)
+        if R:
+            if row_index is not None:
+                rows_gather(f, row_index, out[:, :F])
+            else:
+                copy2d(f, out[:, :F], R, F)
+            copy2d(extra.detach().contiguous(), out[:, F:], R, X)
+        ctx.dims = (int(f.shape[0]), F)
+        ctx.row_index = row_index
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        Nn, F = ctx.dims
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        R = int(d_out.shape[0])
+        if ctx.row_index is not None:
+            d_feat = torch.zeros(Nn, F, device=d_out.device, dtype=torch.float32)
+            if R:
+                rows_scatter(d_out[:, :F], ctx.row_index, d_feat)
+        else:
+            d_feat = torch.empty(Nn, F, device=d_out.device, dtype=torch.float32)
+            if R:
+                copy2d(d_out[:, :F], d_feat, R, F)
+        return d_feat, None, None
+
+
 def edge_attr_fwd(env_id: int, states, edge_index):
     st, ld = _mat(states)
     ei = edge_index.contiguous()

@@ -25,11 +25,18 @@ def set_seed(seed: int):
     torch.cuda.manual_seed_all(seed)
 
 
+# gcbf/trainer/hyperparams.yaml (macbf rows): only the action and h_dot coefficients differ from the gcbf rows
+_MACBF_COEFS = {'SimpleCar': (0.0001, 1.0), 'SimpleDrone': (0.01, 1.0), 'DubinsCar': (0.0005, 1.0)}
+
+
 def read_params(env: str, algo: str) -> Optional[dict]:
     """reference gcbf/trainer/utils.py:317-340 (per-env hyper-parameter table)."""
-    if algo != 'gcbf' or env not in _HYPERPARAMS:
+    if algo not in ('gcbf', 'macbf') or env not in _HYPERPARAMS:
         return None
-    return dict(_HYPERPARAMS[env])
+    hp = dict(_HYPERPARAMS[env])
+    if algo == 'macbf':
+        hp['loss_action_coef'], hp['loss_h_dot_coef'] = _MACBF_COEFS[env]
+    return hp
 
 
 def init_logger(log_path: str, env: str, algo: str, seed: int, args: dict = None, hyper_params: dict = None) -> str:

@@ -214,3 +214,142 @@ def test_kernel_arithmetic_losses_match_autograd(host, E, M, ad, empty):
     assert torch.allclose(d_hn, hn.grad, rtol=1e-5, atol=1e-9)
     assert torch.allclose(d_act, act.grad, rtol=1e-6, atol=1e-9)
     assert partial[7] == E and partial[10] == M
+
+
+# ---- the product's Python on a host emulation of the C ABI (tests/fake_device.py) ------------------------------------------------
+def _product_algo(fix, sb, monkeypatch, host):
+    import fake_device
+    from gcbf_b200.algo import make_algo
+    from gcbf_b200.env import make_env
+    fd = fake_device.install(monkeypatch, host)
+    dev = torch.device('cpu')
+    env = make_env(sb.env, sb.num_agents, dev)
+    params = env.default_params
+    params.update({'num_obs': sb.num_obs, 'area_size': sb.area_size})
+    env = make_env(sb.env, sb.num_agents, dev, params=params, max_neighbors=12)       # train.py:30
+    algo = make_algo('macbf', env, sb.num_agents, env.node_dim, env.edge_dim, env.action_dim, dev, 512, MO.HYPERPARAMS[sb.env])
+    algo.cbf.load_state_dict(fix['cbf_init'])
+    algo.actor.load_state_dict(fix['actor_init'])
+    return fd, env, algo
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_product_python_wiring_on_the_fake_device(host, monkeypatch, case):
+    """algo/macbf.py + the autograd Functions + env glue + flat bucket / optimiser glue, executed on the host emulation of the C ABI,
+    against the reference-on-shim fixture: top-k edges, per-edge h, actions, masks, two train steps (losses, accuracies) and the
+    post-step weights."""
+    from gcbf_b200 import synth
+    fix = load_golden(case)
+    meta, sb = _inputs(fix)
+    fd, env, algo = _product_algo(fix, sb, monkeypatch, host)
+    data = synth.product_batch(env, sb, torch.device('cpu'))
+    assert torch.equal(data.edge_index, fix['edge_index'])
+    assert torch.allclose(data.u_ref, fix['u_ref'], rtol=0, atol=1e-6)
+    assert torch.allclose(data.edge_attr, fix['edge_attr'], rtol=0, atol=0)
+    with torch.no_grad():
+        h, u = algo.cbf(data), algo.act(data)
+    assert torch.allclose(h, fix['h_probe'], rtol=0, atol=1e-6) and torch.allclose(u, fix['u_probe'], rtol=0, atol=1e-6)
+    assert torch.equal(env.safe_mask(data, return_edge=True), fix['safe_mask'])
+    assert torch.equal(env.unsafe_mask(data, return_edge=True), fix['unsafe_mask'])
+    n = sb.num_agents
+    one = synth.product_batch(env, synth.SynthBatch(sb.env, n, sb.num_obs, 1, sb.area_size, sb.states[:sb.nodes_per_graph], sb.goals, sb.obs),
+                              torch.device('cpu'))
+    assert torch.allclose(algo.apply(one), fix['apply_action'], rtol=0, atol=1e-6)
+    for gold in fix['steps']:
+        res = algo.train_step(data)
+        s = res['scalars'].tolist()
+        for i, tag in enumerate(('loss/unsafe', 'loss/safe', 'loss/derivative', 'loss/action', 'acc/unsafe', 'acc/safe')):
+            assert abs(s[i] - gold['scalars'][tag]) <= 2e-6, (tag, s[i], gold['scalars'][tag])
+        assert abs(s[7] - gold['scalars']['acc/derivative']) <= 1e-6
+    assert not digest_close({k: v for k, v in algo.cbf.state_dict().items()}, fix['cbf_final'], 1e-5, 1e-5, flip=3e-6)
+    assert not digest_close({k: v for k, v in algo.actor.state_dict().items()}, fix['actor_final'], 1e-5, 1e-5, flip=3e-6)
+    for name in ('gcbf_radius_graph_topk_count', 'gcbf_radius_graph_topk_fill', 'gcbf_edge_masks', 'gcbf_seg_max_fwd', 'gcbf_seg_max_bwd',
+                 'gcbf_macbf_loss_partials', 'gcbf_macbf_loss_grads', 'gcbf_mlp_forward', 'gcbf_mlp_backward', 'gcbf_clip_adam', 'gcbf_step_bwd',
+                 'gcbf_edge_attr_bwd'):
+        assert name in fd.calls, name
+
+
+def test_factories_and_state_dict_contract():
+    """make_env(max_neighbors) / make_algo('macbf' | 'nominal') exist with the reference's signatures; the MACBF networks carry the
+    reference's state-dict keys and, seeded like the reference (GCBF nets drawn first), its initial weights."""
+    from gcbf_b200.algo import MACBF, Nominal, make_algo
+    from gcbf_b200.env import make_env
+    from gcbf_b200.trainer.utils import read_params
+    fix = load_golden('macbf_dubins_n24_o6_b3')
+    dev = torch.device('cpu')
+    env = make_env('DubinsCar', 24, dev, max_neighbors=12)
+    assert env._max_neighbors == 12
+    with pytest.raises(ValueError):
+        make_env('DubinsCar', 24, dev, max_neighbors=0)
+    torch.manual_seed(0)
+    algo = make_algo('macbf', env, 24, env.node_dim, env.edge_dim, env.action_dim, dev, 512, read_params('DubinsCar', 'macbf'))
+    assert isinstance(algo, MACBF) and algo.params['loss_h_dot_coef'] == 1.0 and algo.params['loss_action_coef'] == 0.0005
+    for mod, key in ((algo.cbf, 'cbf_init'), (algo.actor, 'actor_init')):
+        sd = mod.state_dict()
+        assert list(sd.keys()) == list(fix[key].keys())
+        for k, v in sd.items():
+            assert torch.allclose(v, fix[key][k], rtol=0, atol=1e-6), k      # bit-equal on the same host; LAPACK's QR differs across CPUs
+    fast = MACBF(env, 24, env.node_dim, env.edge_dim, env.action_dim, dev, reference_rng=False)
+    assert list(fast.actor.state_dict().keys()) == list(fix['actor_init'].keys())
+    with pytest.raises(NotImplementedError):
+        algo.use_device_replay()
+    nom = make_algo('nominal', env, 24, env.node_dim, env.edge_dim, env.action_dim, dev)
+    assert isinstance(nom, Nominal)
+    with pytest.raises(NotImplementedError):
+        make_algo('ppo', env, 24, env.node_dim, env.edge_dim, env.action_dim, dev)
+    for e in ('SimpleCar', 'SimpleDrone', 'DubinsCar'):
+        assert read_params(e, 'macbf') == MO.HYPERPARAMS[e]
+
+
+def test_macbf_still_has_no_cpu_fallback():
+    from gcbf_b200.algo import MACBF
+    from gcbf_b200.env import make_env
+    dev = torch.device('cpu')
+    env = make_env('SimpleCar', 8, dev, max_neighbors=12)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        env.graph_from_states(torch.rand(8, 4), with_u_ref=False)
+    algo = MACBF(env, 8, 4, 4, 2, dev, reference_rng=False)
+    from gcbf_b200.data import Data
+    d = Data(x=torch.zeros(8, 4), states=torch.rand(8, 4), edge_index=torch.tensor([[1, 0], [0, 1]]), edge_attr=torch.rand(2, 4), u_ref=torch.zeros(8, 2))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        algo.cbf(d)
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/gcbf_b200.h against the ctypes signature the Python binding registers for it: same number of
+    parameters, same kind (pointer / int32 / int64 / float / double / size_t) in every position, same return kind.  A mismatch would
+    not fail at import -- it would silently shift arguments on the GPU box."""
+    import re
+    from gcbf_b200 import _C, native  # noqa: F401  (native registers the chain-level signatures)
+    text = open(os.path.join(ROOT, 'include', 'gcbf_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
+    protos = re.findall(r'^\s*((?:const\s+)?[\w ]+?\**)\s+(gcbf_\w+)\s*\(([^;{}]*)\)\s*;', text, flags=re.M)
+    assert len(protos) >= 60
+
+    def c_kind(decl):
+        d = decl.strip()
+        if '*' in d or '[' in d:
+            return 'ptr'
+        d = re.sub(r'\b\w+$', '', d).strip() if len(d.split()) > 1 else d      # drop the parameter name
+        d = d.replace('const', '').strip()
+        return {'int': 'i32', 'int32_t': 'i32', 'int64_t': 'i64', 'long long': 'i64', 'unsigned long long': 'i64', 'float': 'f32',
+                'double': 'f64', 'size_t': 'size', 'void': 'void', 'char': 'i8'}[d]
+
+    def py_kind(t):
+        if t is None:
+            return 'void'
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or issubclass(t, ctypes._Pointer):
+            return 'ptr'
+        return {ctypes.c_int: 'i32', ctypes.c_int32: 'i32', ctypes.c_int64: 'i64', ctypes.c_longlong: 'i64', ctypes.c_ulonglong: 'i64',
+                ctypes.c_float: 'f32', ctypes.c_double: 'f64', ctypes.c_size_t: 'size'}[t]
+
+    seen = set()
+    for ret, name, params in protos:
+        assert name in _C._SIGS, f'{name} is declared in the header but has no ctypes signature'
+        seen.add(name)
+        res, args = _C._SIGS[name]
+        want = [] if params.strip() in ('', 'void') else [c_kind(p) for p in params.split(',')]
+        got = [py_kind(a) for a in args]
+        assert got == want, f'{name}: header {want} vs ctypes {got}'
+        assert py_kind(res) == c_kind(ret + ' x'), name
+    assert set(_C._SIGS) <= seen, set(_C._SIGS) - seen
