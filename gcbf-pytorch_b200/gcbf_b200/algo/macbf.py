@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from .. import _C
+from .. import _C, ops
 from ..controller import MACBFController
 from ..data import Batch
 from ..nn import CBFNetLayer, GraphSequential
@@ -38,6 +38,7 @@ class CBFNet(nn.Module):
 
 
 class MACBF(GCBF):
+    GRAD_INTO_PARAM = True      # False: the MLP weight gradients travel back through autograd (A/B switch, tests run both)
 
     def __init__(self, env, num_agents: int, node_dim: int, edge_dim: int, action_dim: int, device: torch.device,
                  batch_size: int = 500, params: Optional[dict] = None, reference_rng: bool = True):
@@ -103,11 +104,17 @@ class MACBF(GCBF):
                 float(hp['loss_h_dot_coef']), float(hp['loss_action_coef']), _C.ptr(partial), _C.ptr(d_h), _C.ptr(d_hn), _C.ptr(d_act),
                 _C.ptr(scalars))
         bucket.zero_grad()                                               # macbf.py:179-180
-        # the parameters' .grad are views into the flat bucket: autograd accumulates the MLP weight gradients there in place
-        if E:
-            torch.autograd.backward([h, h_next, actions], [d_h, d_hn, d_act])          # macbf.py:181
-        else:
-            torch.autograd.backward([actions], [d_act])
+        # the parameters' .grad are views into the flat bucket.  GRAD_INTO_PARAM: the weight-grad kernels of gcbf_mlp_backward accumulate
+        # straight into them and autograd sees no parameter gradients (otherwise autograd adds each returned gradient with an ATen
+        # kernel: 37 extra launches per step)
+        ops.GRAD_INTO_PARAM = self.GRAD_INTO_PARAM
+        try:
+            if E:
+                torch.autograd.backward([h, h_next, actions], [d_h, d_hn, d_act])      # macbf.py:181
+            else:
+                torch.autograd.backward([actions], [d_act])
+        finally:
+            ops.GRAD_INTO_PARAM = False
         red.sum_(bucket.grad)
         if apply_optim:
             self.optim_step()                                            # macbf.py:182-186: clip(1e-3) per net + Adam, fused

@@ -233,8 +233,9 @@ def _product_algo(fix, sb, monkeypatch, host):
     return fd, env, algo
 
 
+@pytest.mark.parametrize('into_param', [True, False])
 @pytest.mark.parametrize('case', CASES)
-def test_product_python_wiring_on_the_fake_device(host, monkeypatch, case):
+def test_product_python_wiring_on_the_fake_device(host, monkeypatch, case, into_param):
     """algo/macbf.py + the autograd Functions + env glue + flat bucket / optimiser glue, executed on the host emulation of the C ABI,
     against the reference-on-shim fixture: top-k edges, per-edge h, actions, masks, two train steps (losses, accuracies) and the
     post-step weights."""
@@ -242,6 +243,7 @@ def test_product_python_wiring_on_the_fake_device(host, monkeypatch, case):
     fix = load_golden(case)
     meta, sb = _inputs(fix)
     fd, env, algo = _product_algo(fix, sb, monkeypatch, host)
+    algo.GRAD_INTO_PARAM = into_param
     data = synth.product_batch(env, sb, torch.device('cpu'))
     assert torch.equal(data.edge_index, fix['edge_index'])
     assert torch.allclose(data.u_ref, fix['u_ref'], rtol=0, atol=1e-6)

@@ -39,12 +39,14 @@ def _env_algo(sb, fix=None, k=12):
     return env, algo
 
 
+@pytest.mark.parametrize('into_param', [True, False])
 @pytest.mark.parametrize('case', CASES)
-def test_macbf_forward_and_train_steps_match_the_reference(case):
+def test_macbf_forward_and_train_steps_match_the_reference(case, into_param):
     from gcbf_b200 import synth
     fix = load_golden(case)
     meta, sb = _inputs(fix)
     env, algo = _env_algo(sb, fix)
+    algo.GRAD_INTO_PARAM = into_param        # weight gradients accumulated by the kernels / returned through autograd
     data = synth.product_batch(env, sb, DEV)
     assert torch.equal(data.edge_index.cpu(), fix['edge_index'])                        # top-k filtered radius graph: bit-exact
     assert torch.allclose(data.edge_attr.cpu(), fix['edge_attr'], rtol=0, atol=1e-6)
