@@ -540,6 +540,37 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_macbf(args):
+    """`--macbf`: the MACBF baseline's train step (not the headline metric) at the reference's own training scale and at
+    C3's shape, device-timed (tools/macbf_probe.py), with the CPU port of the same step timed beside it on the first workload."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import macbf_probe
+    dev = torch.device('cuda', 0)
+    out = {}
+    for name in macbf_probe.WORKLOADS:
+        rec, (sb, algo, data) = macbf_probe.measure(name, dev, steps=max(args.steps, 10), warmup=max(args.warmup, 3))
+        if name == 'ref' and not args.no_cpu_baseline:
+            host_threads()
+            sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+            import macbf_oracle as MO                # CPU baseline leg: the only use of oracle/ on this path
+            cbf = {k: v.detach().cpu().clone() for k, v in algo.cbf.state_dict().items()}
+            act = {k: v.detach().cpu().clone() for k, v in algo.actor.state_dict().items()}
+            ei, ur = data.edge_index.cpu(), data.u_ref.cpu()
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                MO.update_step(sb.env, cbf, act, {}, {}, sb.states, sb.goals, ei, ur, sb.num_graphs, sb.num_agents, sb.num_obs)
+                ts.append(time.perf_counter() - t0)
+            t = statistics.median(ts)
+            rec['cpu_baseline'] = {'value': round(rec['agents'] / t, 1), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                                   'sample': f'the same batch (graph given), median of 5 steps, {t:.3f} s/step'}
+        out[name] = rec
+    print(json.dumps({'metric': 'agent*steps/sec (MACBF train step, device-timed)', 'unit': UNIT, 'n_gpus': 1, 'higher_is_better': True,
+                      'data': 'synthetic', 'dtype': 'f32', 'value': out['ref']['agent_steps_per_s'], 'ms_per_step': out['ref']['train_step_ms'],
+                      'config': {'workload': 'MACBF ' + out['ref']['workload'], 'also': {'C3': out['C3']}},
+                      'gpu_launches': out['ref']['gpu_launches_per_step'], 'cpu_baseline': out['ref'].get('cpu_baseline'), 'detail': out['ref']}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -550,13 +581,17 @@ def main():
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg (profiling runs under ncu only)')
+    ap.add_argument('--macbf', action='store_true', help='measure the MACBF baseline train step instead (SURVEY 8f-4; single GPU, own arm only)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit('bench.py (own arm) needs a CUDA device: the gcbf_b200 path has no CPU fallback')
-        run_own(args)
+        if args.macbf:
+            run_macbf(args)
+        else:
+            run_own(args)
 
 
 if __name__ == '__main__':

@@ -1,12 +1,12 @@
 """MACBF baseline on the GPU: train-step time (forward + losses + backward + clip + Adam), graph build with the top-12
-filter and the actor's rollout-time latency on synthetic batches, with the CPU port (oracle/macbf_oracle.py) timed beside it on a
-bounded sample.  Device-timed with CUDA events after warm-up.
+filter and the actor's rollout-time latency on synthetic batches.  Device-timed with CUDA events after warm-up.  (`bench.py --macbf`
+prints the same measurement as a bench line with the CPU port timed beside it; this tool never touches oracle/.)
     python tools/macbf_probe.py [out.json]           # both workloads
-    python tools/macbf_probe.py --one-step C3        # one train step only (for an ncu capture of the same command)
+    python tools/macbf_probe.py --one-step C3        # two train steps only (for an ncu capture of the same command)
 """
-import json, os, sys, time, torch
+import json, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [os.path.join(ROOT, 'gcbf-pytorch_b200'), os.path.join(ROOT, 'oracle'), ROOT]
+sys.path[:0] = [os.path.join(ROOT, 'gcbf-pytorch_b200'), ROOT]
 from gcbf_b200 import _C, synth
 from gcbf_b200.algo import MACBF
 from gcbf_b200.env import make_env
@@ -44,6 +44,26 @@ def timed(fn, steps, warmup):
     return a.elapsed_time(b) / steps
 
 
+def measure(name, dev, steps=20, warmup=5):
+    """(record, (sb, algo, data)) for one workload."""
+    sb, env, algo = build(name, dev)
+    st = sb.states.to(dev)
+    data = synth.product_batch(env, sb, dev)
+    E, M = int(data.edge_index.shape[1]), int(data.u_ref.shape[0])
+    _C.reset_counters()
+    algo.train_step(data)
+    launches = _C.kernel_launches()
+    ms_step = timed(lambda: algo.train_step(data), steps, warmup)
+    ms_graph = timed(lambda: env.graph_from_states(st), steps, 3)
+    with torch.no_grad():
+        ms_act = timed(lambda: algo.act(data), steps, 3)
+    rec = dict(workload=f"{sb.env} n={sb.num_agents} obs={sb.num_obs} B={sb.num_graphs} area={sb.area_size} max_neighbors=12", agents=M, edges=E,
+               max_in_degree=int(torch.bincount(data.edge_index[1]).max()), train_step_ms=round(ms_step, 4),
+               agent_steps_per_s=round(M / ms_step * 1e3, 1), graph_build_ms=round(ms_graph, 4), actor_forward_ms=round(ms_act, 4),
+               gpu_launches_per_step=int(launches), loss=float(algo.train_step(data)['scalars'][6]))
+    return rec, (sb, algo, data)
+
+
 def main():
     dev = torch.device('cuda', 0)
     if len(sys.argv) > 1 and sys.argv[1] == '--one-step':
@@ -56,38 +76,8 @@ def main():
         return
     out = {}
     for name in WORKLOADS:
-        sb, env, algo = build(name, dev)
-        st = sb.states.to(dev)
-        data = synth.product_batch(env, sb, dev)
-        E, M = int(data.edge_index.shape[1]), int(data.u_ref.shape[0])
-        _C.reset_counters()
-        algo.train_step(data)
-        launches = _C.kernel_launches()
-        ms_step = timed(lambda: algo.train_step(data), 20, 5)
-        ms_graph = timed(lambda: env.graph_from_states(st), 20, 3)
-        with torch.no_grad():
-            ms_act = timed(lambda: algo.act(data), 20, 3)
-        rec = dict(workload=f"{sb.env} n={sb.num_agents} obs={sb.num_obs} B={sb.num_graphs} area={sb.area_size} max_neighbors=12", agents=M, edges=E,
-                   max_in_degree=int(torch.bincount(data.edge_index[1]).max()), train_step_ms=round(ms_step, 4),
-                   agent_steps_per_s=round(M / ms_step * 1e3, 1), graph_build_ms=round(ms_graph, 4), actor_forward_ms=round(ms_act, 4),
-                   gpu_launches_per_step=int(launches), loss=float(algo.train_step(data)['scalars'][6]))
-        if name == 'ref':
-            # CPU port on the same batch (a bounded sample: 3 steps), all host threads the container may use
-            import gcbf_oracle as O, macbf_oracle as MO
-            import bench
-            torch.set_num_threads(bench.host_threads())
-            cbf = {k: v.detach().cpu().clone() for k, v in algo.cbf.state_dict().items()}
-            act = {k: v.detach().cpu().clone() for k, v in algo.actor.state_dict().items()}
-            ei, ur = data.edge_index.cpu(), data.u_ref.cpu()
-            ts = []
-            for _ in range(3):
-                t0 = time.perf_counter()
-                MO.update_step(sb.env, cbf, act, {}, {}, sb.states, sb.goals, ei, ur, sb.num_graphs, sb.num_agents, sb.num_obs)
-                ts.append(time.perf_counter() - t0)
-            rec['cpu_port'] = dict(seconds_per_step=round(sorted(ts)[1], 4), agent_steps_per_s=round(M / sorted(ts)[1], 1), cores=torch.get_num_threads(),
-                                   sample='the same batch, median of 3 steps, graph given')
-        out[name] = rec
-        print(json.dumps({name: rec}))
+        out[name] = measure(name, dev)[0]
+        print(json.dumps({name: out[name]}))
     if len(sys.argv) > 1:
         json.dump(out, open(sys.argv[1], 'w'), indent=1)
 
