@@ -98,24 +98,14 @@ class FakeDevice:
                                    ctypes.c_int64(E))
 
     def gcbf_macbf_loss_partials(self, h, hn, safe, unsafe, E, act, ad, M, alpha, eps, dt, partial):
-        self._loss(h, hn, safe, unsafe, E, act, ad, M, alpha, eps, dt, 1.0, 1.0, 1.0, 1.0, partial, None, None, None, None)
+        f, P = ctypes.c_float, ctypes.c_void_p
+        self.host.host_macbf_loss_partials(P(h), P(hn), P(safe), P(unsafe), ctypes.c_int64(E), P(act), ad, ctypes.c_int64(M), f(alpha), f(eps), f(dt),
+                                           P(partial))
 
     def gcbf_macbf_loss_grads(self, h, hn, safe, unsafe, E, act, ad, M, alpha, eps, dt, cu, cs, ch, ca, partial, d_h, d_hn, d_act, scalars):
-        self._loss(h, hn, safe, unsafe, E, act, ad, M, alpha, eps, dt, cu, cs, ch, ca, None, d_h, d_hn, d_act, scalars, check=partial)
-
-    def _loss(self, h, hn, safe, unsafe, E, act, ad, M, alpha, eps, dt, cu, cs, ch, ca, partial, d_h, d_hn, d_act, scalars, check=None):
-        p = torch.zeros(16, dtype=torch.float64)
-        gh, ghn, ga, sc = torch.zeros(max(E, 1)), torch.zeros(max(E, 1)), torch.zeros(max(M * ad, 1)), torch.zeros(8)
-        f = ctypes.c_float
-        self.host.host_macbf_loss(ctypes.c_void_p(h), ctypes.c_void_p(hn), ctypes.c_void_p(safe), ctypes.c_void_p(unsafe), ctypes.c_int64(E),
-                                  ctypes.c_void_p(act), ad, ctypes.c_int64(M), f(alpha), f(eps), f(dt), f(cu), f(cs), f(ch), f(ca),
-                                  ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(gh.data_ptr()), ctypes.c_void_p(ghn.data_ptr()),
-                                  ctypes.c_void_p(ga.data_ptr()), ctypes.c_void_p(sc.data_ptr()))
-        if partial is not None:
-            V(partial, 16, torch.float64).copy_(p)
-            return
-        assert torch.equal(V(check, 16, torch.float64), p)       # single process: the partial sums come back unchanged
-        V(d_h, E).copy_(gh[:E]); V(d_hn, E).copy_(ghn[:E]); V(d_act, M * ad).copy_(ga[:M * ad]); V(scalars, 8).copy_(sc)
+        f, P = ctypes.c_float, ctypes.c_void_p             # `partial` may have been all-reduced over ranks in between
+        self.host.host_macbf_loss_grads(P(h), P(hn), P(safe), P(unsafe), ctypes.c_int64(E), P(act), ad, ctypes.c_int64(M), f(alpha), f(eps), f(dt),
+                                        f(cu), f(cs), f(ch), f(ca), P(partial), P(d_h), P(d_hn), P(d_act), P(scalars))
 
     def gcbf_edge_attr_fwd(self, env, states, ld, edge_index, E, out):
         if E == 0:

@@ -49,12 +49,17 @@ void host_seg_max_bwd(const float* d_out, int ld_dout, const int32_t* argmax, in
     }
 }
 
-void host_macbf_loss(const float* h, const float* hn, const uint8_t* safe, const uint8_t* unsafe, int64_t E, const float* act, int ad, int64_t M,
-                     float alpha, float eps, float dt, float cu, float cs, float ch, float ca, double* partial, float* d_h, float* d_hn,
-                     float* d_act, float* scalars) {
+// the two passes of gcbf_macbf_loss_partials / gcbf_macbf_loss_grads (ranks may all-reduce `partial` in between)
+void host_macbf_loss_partials(const float* h, const float* hn, const uint8_t* safe, const uint8_t* unsafe, int64_t E, const float* act, int ad,
+                              int64_t M, float alpha, float eps, float dt, double* partial) {
   for (int k = 0; k < MLP_SIZE; ++k) partial[k] = 0.0;
   for (int64_t e = 0; e < E; ++e) edge_terms(h[e], hn[e], safe[e], unsafe[e], alpha, eps, dt, partial);
   for (int64_t i = 0; i < M; ++i) { partial[MLP_SUM_ACT] += action_term(act + i * ad, ad); partial[MLP_CNT_AGENTS] += 1.0; }
+}
+
+void host_macbf_loss_grads(const float* h, const float* hn, const uint8_t* safe, const uint8_t* unsafe, int64_t E, const float* act, int ad, int64_t M,
+                           float alpha, float eps, float dt, float cu, float cs, float ch, float ca, const double* partial, float* d_h, float* d_hn,
+                           float* d_act, float* scalars) {
   const double cnt_u = partial[MLP_CNT_UNSAFE], cnt_s = partial[MLP_CNT_SAFE], cnt_e = partial[MLP_CNT_EDGES], cnt_a = partial[MLP_CNT_AGENTS];
   const float inv_u = cnt_u > 0 ? (float)(1.0 / cnt_u) : 0.f, inv_s = cnt_s > 0 ? (float)(1.0 / cnt_s) : 0.f;
   const float inv_e = cnt_e > 0 ? (float)(1.0 / cnt_e) : 0.f, inv_a = cnt_a > 0 ? (float)(1.0 / cnt_a) : 0.f;

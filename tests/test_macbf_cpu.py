@@ -206,10 +206,12 @@ def test_kernel_arithmetic_losses_match_autograd(host, E, M, ad, empty):
     hd, hnd, ad_ = h.detach().contiguous(), hn.detach().contiguous(), act.detach().contiguous()
     s8, u8 = safe.to(torch.uint8), unsafe.to(torch.uint8)
     f = ctypes.c_float
-    host.host_macbf_loss(_p(hd), _p(hnd), _p(s8), _p(u8), ctypes.c_int64(E), _p(ad_), ctypes.c_int(ad), ctypes.c_int64(M), f(alpha), f(eps), f(dt),
-                         f(cu), f(cs), f(ch), f(ca), _p(partial), _p(d_h), _p(d_hn), _p(d_act), _p(sc))
+    host.host_macbf_loss_partials(_p(hd), _p(hnd), _p(s8), _p(u8), ctypes.c_int64(E), _p(ad_), ctypes.c_int(ad), ctypes.c_int64(M), f(alpha), f(eps),
+                                  f(dt), _p(partial))
+    host.host_macbf_loss_grads(_p(hd), _p(hnd), _p(s8), _p(u8), ctypes.c_int64(E), _p(ad_), ctypes.c_int(ad), ctypes.c_int64(M), f(alpha), f(eps), f(dt),
+                               f(cu), f(cs), f(ch), f(ca), _p(partial), _p(d_h), _p(d_hn), _p(d_act), _p(sc))
     for got, want in zip(sc.tolist(), [lu, ls, lh, la, acc[0], acc[1], loss, acc[2]]):
-        assert abs(got - float(want)) <= 1e-6
+        assert abs(got - float(torch.as_tensor(want).detach())) <= 1e-6
     assert torch.allclose(d_h, h.grad, rtol=1e-5, atol=1e-9)
     assert torch.allclose(d_hn, hn.grad, rtol=1e-5, atol=1e-9)
     assert torch.allclose(d_act, act.grad, rtol=1e-6, atol=1e-9)
@@ -355,3 +357,72 @@ def test_ctypes_signatures_match_the_header():
         assert got == want, f'{name}: header {want} vs ctypes {got}'
         assert py_kind(res) == c_kind(ret + ' x'), name
     assert set(_C._SIGS) <= seen, set(_C._SIGS) - seen
+
+
+# ---- data-parallel MACBF step: two gloo ranks on the fake device == one process ---------------------------------------------------
+class _Setter:
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+def _dp_worker(rank, world, port, so_path, case, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import fake_device
+        from gcbf_b200 import synth
+        from gcbf_b200.algo import make_algo
+        from gcbf_b200.distributed import shard_range
+        from gcbf_b200.env import make_env
+        torch.set_num_threads(1)
+        lib = ctypes.CDLL(so_path)
+        lib.host_radius_graph_topk.restype = ctypes.c_int64
+        fake_device.install(_Setter(), lib)
+        fix = load_golden(case)
+        meta, sb = _inputs(fix)
+        dev = torch.device('cpu')
+        env = make_env(sb.env, sb.num_agents, dev)
+        params = env.default_params
+        params.update({'num_obs': sb.num_obs, 'area_size': sb.area_size})
+        env = make_env(sb.env, sb.num_agents, dev, params=params, max_neighbors=12)
+        algo = make_algo('macbf', env, sb.num_agents, env.node_dim, env.edge_dim, env.action_dim, dev, 512, MO.HYPERPARAMS[sb.env])
+        algo.cbf.load_state_dict(fix['cbf_init'])
+        algo.actor.load_state_dict(fix['actor_init'])
+        lo, hi = shard_range(sb.num_graphs, world, rank)            # 3 graphs on 2 ranks: unequal shares
+        N = sb.nodes_per_graph
+        mine = synth.SynthBatch(sb.env, sb.num_agents, sb.num_obs, hi - lo, sb.area_size, sb.states[lo * N:hi * N].contiguous(), sb.goals, sb.obs)
+        data = synth.product_batch(env, mine, dev)
+        scal = [algo.train_step(data)['scalars'].tolist() for _ in fix['steps']]
+        torch.save(dict(scalars=scal, cbf={k: v.clone() for k, v in algo.cbf.state_dict().items()},
+                        actor={k: v.clone() for k, v in algo.actor.state_dict().items()}, share=(lo, hi)), os.path.join(out_dir, f'r{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_equal_one_process(host, tmp_path):
+    """Environment-parallel MACBF: each rank steps its own graphs, the 16 partial sums are all-reduced before the loss gradients are
+    formed and the flat gradient bucket after the backward, so both ranks must report the single-process losses / accuracies (= the
+    reference's, from the fixture) and end with identical weights equal to the single-process ones."""
+    import socket
+    import torch.multiprocessing as mp
+    case = 'macbf_dubins_n24_o6_b3'
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    so_path = os.path.join(ROOT, 'tests', 'host_driver', '_build', 'macbf_host.so')
+    mp.spawn(_dp_worker, args=(2, port, so_path, case, str(tmp_path)), nprocs=2, join=True)
+    fix = load_golden(case)
+    r0, r1 = (torch.load(os.path.join(tmp_path, f'r{r}.pt'), weights_only=False) for r in (0, 1))
+    assert r0['share'] == (0, 2) and r1['share'] == (2, 3)
+    for res in (r0, r1):
+        for s, gold in zip(res['scalars'], fix['steps']):
+            for i, tag in enumerate(('loss/unsafe', 'loss/safe', 'loss/derivative', 'loss/action', 'acc/unsafe', 'acc/safe')):
+                assert abs(s[i] - gold['scalars'][tag]) <= 2e-6, (tag, s[i], gold['scalars'][tag])
+            assert abs(s[7] - gold['scalars']['acc/derivative']) <= 1e-6
+        assert not digest_close(res['cbf'], fix['cbf_final'], 1e-5, 1e-5, flip=3e-6)
+        assert not digest_close(res['actor'], fix['actor_final'], 1e-5, 1e-5, flip=3e-6)
+    for k in r0['cbf']:
+        assert torch.equal(r0['cbf'][k], r1['cbf'][k]), k               # replicas stay bit-identical
+    for k in r0['actor']:
+        assert torch.equal(r0['actor'][k], r1['actor'][k]), k
