@@ -321,7 +321,10 @@ def run_own(args):
     dev = torch.device('cuda', local_rank)
     main_cfg = args.config
     if args.also == 'auto':
-        also = [c for c in (['C2'] + (['C4', 'C5'] if world == 8 else [])) if c != main_cfg]
+        # one GPU: every other BASELINE config as its per-GPU share (C1; C2; C4 = 2 of the 16 replicas; C5 = 1 of the 8 dense graphs), so
+        # that the single-GPU line carries the whole config table; 8 GPUs: the two configs BASELINE defines over 8 GPUs
+        extra_cfgs = ['C2', 'C1', 'C4', 'C5'] if world == 1 else (['C2', 'C4', 'C5'] if world == 8 else ['C2'])
+        also = [c for c in extra_cfgs if c != main_cfg]
     else:
         also = [c for c in args.also.split(',') if c and c != 'none' and c != main_cfg]
 
@@ -330,7 +333,15 @@ def run_own(args):
     m = measure(main_cfg, args, dev, rank, world, dist, True, sampler)
     extra = {}
     for c in also:
-        r = measure(c, args, dev, rank, world, dist, False, None)
+        if world == 1:
+            try:                                                  # an extra config never costs the headline line (single process: no
+                r = measure(c, args, dev, rank, world, dist, False, None)      # collective another rank could be left waiting in)
+            except Exception as ex:
+                extra[c] = {'error': repr(ex)[:300]}
+                torch.cuda.synchronize()
+                continue
+        else:
+            r = measure(c, args, dev, rank, world, dist, False, None)
         agents_c = r['B'] * r['n'] * world
         extra[c] = {'workload': f"{c}: {r['sb'].env} n={r['n']} obs={r['sb'].num_obs} B={r['B']}/GPU area={r['sb'].area_size}",
                     'agents_per_step': agents_c, 'edges_per_step': r['E_total'], 'ms_per_step': round(r['ms'] / args.steps, 4),
