@@ -338,7 +338,6 @@ def run_own(args):
                 r = measure(c, args, dev, rank, world, dist, False, None)      # collective another rank could be left waiting in)
             except Exception as ex:
                 extra[c] = {'error': repr(ex)[:300]}
-                torch.cuda.synchronize()
                 continue
         else:
             r = measure(c, args, dev, rank, world, dist, False, None)
