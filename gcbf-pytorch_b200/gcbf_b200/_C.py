@@ -85,6 +85,10 @@ _SIGS = {
     'gcbf_seg_max_fwd': (c_int, [P, c_int, P, c_int, c_int, P, c_int, P, P]),
     'gcbf_seg_max_bwd': (c_int, [P, c_int, P, c_int, c_int, P, c_int, c_int64, P]),
     'gcbf_macbf_loss_partials': (c_int, [P, P, P, P, c_int64, P, c_int, c_int64, c_float, c_float, c_float, P, P]),
+    # analytic h_dot (csrc/jvp.cu)
+    'gcbf_state_dot': (c_int, [POINTER(EnvCfg), P, c_int, P, P, P, c_int, c_int, c_int, P, c_int, P]),
+    'gcbf_edge_attr_tangent': (c_int, [c_int, P, c_int, P, c_int, P, c_int64, P, P]),
+    'gcbf_attn_aggr_tangent': (c_int, [P, c_int, P, c_int, P, P, P, c_int, c_int, P, c_int, P]),
     'gcbf_macbf_loss_grads': (c_int, [P, P, P, P, c_int64, P, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_float,
                                       c_float, P, P, P, P, P, P]),
 }

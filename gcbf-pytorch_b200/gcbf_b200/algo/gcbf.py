@@ -555,6 +555,16 @@ class GCBF(Algorithm):
         self.last_apply_rounds = rounds.value
         return action
 
+    # ---- analytic h_dot (additive: the training loss keeps the reference's finite difference) ------------------
+    def h_dot_analytic(self, data, action: Optional[Tensor] = None, freeze: Optional[bool] = None):
+        """(h, h_dot) with h_dot_i = sum_k dh_i/ds_k . f(s_k, clamp(u_k + u_ref)) as one forward-mode pass (gcbf_b200/jvp.py): the
+        derivative the finite difference (h(x + dt f) - h(x)) / dt of gcbf.py:193-207 approximates, edges held fixed.  action: the
+        policy's correction (default: the actor's).  The CBF condition of the paper is h_dot + alpha h >= 0."""
+        from .. import jvp
+        if action is None:
+            action = self.act(data)
+        return jvp.cbf_value_and_h_dot(self.cbf, self._env, data, action, freeze)
+
     # ---- checkpoints (file names and keys of gcbf.py:249-258) ------------------------------------------
     def save(self, save_dir: str):
         os.makedirs(save_dir, exist_ok=True)

@@ -473,6 +473,23 @@ int gcbf_macbf_loss_grads(const float* h, const float* h_next, const uint8_t* sa
                           float coef_unsafe, float coef_safe, float coef_hdot, float coef_action, const double* partial, float* d_h,
                           float* d_h_next, float* d_action, float* scalars, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Analytic h_dot (an ADDITIVE alternative to the finite difference of gcbf/algo/gcbf.py:193-207, not used by the
+ * training loss): h_dot_i = sum_k (dh_i/ds_k) . f(s_k, u_k) with the edges held fixed, as a forward-mode pass.  The linear layers
+ * of the tangent reuse gcbf_linear_fwd* (no bias, no activation) and gcbf_act_bwd (activation derivative); the other pieces:
+ *   gcbf_state_dot         x_dot = f(x, clamp(action + u_ref)) for every node (dynamics of simple_car.py:78-89, dubins_car.py:110-132,
+ *                          simple_drone.py:103-120; u_ref [num_graphs * num_agents, a] from gcbf_u_ref; freeze != 0: the single-graph
+ *                          reach-freeze, needs goal [num_agents, >= pos_dim] (goal_per_graph != 0: one goal set per graph))
+ *   gcbf_edge_attr_tangent d/dt edge_attr = g'(s_j) s_dot_j - g'(s_i) s_dot_i            [E, edge_dim]
+ *   gcbf_attn_aggr_tangent d/dt sum_e softmax(gate)_e msg_e given d msg [E, C], d gate [E] and the forward's att [E]
+ * ------------------------------------------------------------------------------------------------- */
+int gcbf_state_dot(const gcbf_env_cfg* cfg, const float* states, int ld_state, const float* action, const float* u_ref,
+                   const float* goal, int ld_goal, int goal_per_graph, int freeze, float* state_dot, int ld_out, void* stream);
+int gcbf_edge_attr_tangent(int env, const float* states, int ld_state, const float* state_dot, int ld_sdot, const int64_t* edge_index,
+                           int64_t num_edges, float* t_edge_attr, void* stream);
+int gcbf_attn_aggr_tangent(const float* msg, int ld_msg, const float* t_msg, int ld_tmsg, const float* att, const float* t_gate,
+                           const int32_t* rowptr, int num_nodes, int channels, float* t_aggr, int ld_taggr, void* stream);
+
 /* instrumentation (bench.py): kernels launched by the chain-level calls since the last reset, and optional CUDA-event timing of
  * every linear-layer launch (kind 0 forward / 1 data-grad / 2 weight-grad on the tensor cores, 3 fp32 linear kernels, 4 operand
  * preparation = amax + fp16 split) */

@@ -191,6 +191,59 @@ class FakeDevice:
         bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
         P_.addcdiv_(M_, (V_.sqrt() / math.sqrt(bc2)).add_(eps), value=-lr / bc1)
 
+    # ---- analytic h_dot: the Python-sequenced primal forward (ops.net_forward) + the tangent kernels (host build of jvp_core.h) ------
+    def gcbf_linear_fwd(self, X, ldx, W, ldw, bias, inv_sigma, Y, ldy, M, N, K, act, impl, out_amax):
+        if M == 0:
+            return
+        alpha = float(V(inv_sigma, 1)[0]) if inv_sigma else 1.0
+        y = alpha * (T(X, M, ldx, K) @ T(W, N, ldw, K).t())
+        if bias:
+            y = y + V(bias, N)
+        y = torch.relu(y) if act == 1 else (torch.tanh(y) if act == 2 else y)
+        T(Y, M, ldy, N).copy_(y)
+
+    def gcbf_act_bwd(self, dY, Y, dZ, count, act):
+        assert dY and Y and dZ, 'gcbf_act_bwd rejects null pointers even for count 0'
+        g, y = V(dY, count), V(Y, count)
+        V(dZ, count).copy_(g * (1 - y * y) if act == 2 else (g * (y > 0) if act == 1 else g))
+
+    def gcbf_attn_aggr_fwd(self, msg, ld_msg, gate, rowptr, num_nodes, C, att, aggr, ld_aggr):
+        assert C == 256 and ld_msg % 4 == 0 and ld_aggr % 4 == 0
+        rp = V(rowptr, num_nodes + 1, torch.int32).long()
+        E = int(rp[-1])
+        out = T(aggr, num_nodes, ld_aggr, C)
+        out.zero_()
+        if E == 0:
+            return
+        dst = torch.repeat_interleave(torch.arange(num_nodes), rp[1:] - rp[:-1])
+        a = O.segment_softmax(V(gate, E).reshape(-1, 1).clone(), dst, num_nodes)
+        V(att, E).copy_(a.reshape(-1))
+        out.copy_(torch.zeros(num_nodes, C).index_add(0, dst, a * T(msg, E, ld_msg, C)))
+
+    def gcbf_sn_power_iter_batched(self, arr, count, ws, ws_floats):
+        import torch.nn.functional as F
+        for i in range(count):
+            a = arr[i]
+            W, u, v = T(a.W, a.N, a.ldw, a.K), V(a.u, a.N), V(a.v, a.K)
+            v.copy_(F.normalize(torch.mv(W.t(), u), dim=0, eps=1e-12))
+            u.copy_(F.normalize(torch.mv(W, v), dim=0, eps=1e-12))
+            V(a.inv_sigma, 1)[0] = 1.0 / float(torch.dot(u, torch.mv(W, v)))
+
+    def gcbf_state_dot(self, cfg, states, ld, action, u_ref, goal, ldg, goal_per_graph, freeze, out, ld_out):
+        c = cfg._obj
+        lim = 2.0 if c.env == 1 else 10.0
+        f, P = ctypes.c_float, ctypes.c_void_p
+        self.jvp_host.host_state_dot(c.env, c.num_graphs, c.nodes_per_graph, c.num_agents, P(states), ld, P(action), P(u_ref), P(goal), ldg,
+                                     c.num_agents if goal_per_graph else 0, f(lim), f(c.speed_limit), f(c.dist2goal), freeze, P(out), ld_out)
+
+    def gcbf_edge_attr_tangent(self, env, states, ld, sdot, ld_sd, edge_index, E, out):
+        P = ctypes.c_void_p
+        self.jvp_host.host_edge_attr_tangent(env, P(states), ld, P(sdot), ld_sd, P(edge_index), ctypes.c_int64(E), P(out))
+
+    def gcbf_attn_aggr_tangent(self, msg, ld_msg, t_msg, ld_tmsg, att, t_gate, rowptr, num_nodes, C, out, ld_out):
+        P = ctypes.c_void_p
+        self.jvp_host.host_attn_aggr_tangent(P(msg), ld_msg, P(t_msg), ld_tmsg, P(att), P(t_gate), P(rowptr), num_nodes, C, P(out), ld_out)
+
     # ---- chain-level MLP (what native.fn(...) returns) ------------------------------------------------------------------------
     def _layers(self, arr, n):
         out = []
@@ -238,10 +291,26 @@ class FakeDevice:
         return 0
 
 
-def install(monkeypatch, host_lib):
+class _NoStream:
+    def wait_event(self, ev):
+        pass
+
+
+class _NoEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a, **k):
+        pass
+
+
+def install(monkeypatch, host_lib, jvp_host_lib=None):
     """Route the product's C-ABI calls to a FakeDevice for the duration of a test.  Returns the FakeDevice."""
     from gcbf_b200 import _C, native, ops
     fd = FakeDevice(host_lib)
+    fd.jvp_host = jvp_host_lib
+    monkeypatch.setattr(torch.cuda, 'Event', _NoEvent)                    # ops.sn_power_iter_batched orders its iterations with events
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: _NoStream())
 
     def call(name, *args):
         fn = getattr(fd, name, None)
