@@ -75,6 +75,8 @@ class MLP(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         specs = self.specs()
         lead = x.shape[:-1]
+        if x.numel() == 0:        # no rows (e.g. the edge MLP of a graph without edges): nothing to launch, no gradient to anybody
+            return x.new_zeros(*lead, int(specs[-1].W.shape[0]))
         if not torch.is_grad_enabled() and ops.NATIVE and len(specs) <= ops.native.MAX_LAYERS and x.is_cuda:
             y = ops.native_mlp_forward(x.reshape(-1, x.shape[-1]), specs, False)[0]      # inference: nothing saved (see gnn.py run())
         else:

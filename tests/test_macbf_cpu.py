@@ -10,7 +10,6 @@ import ctypes
 import os
 import subprocess
 
-import numpy as np
 import pytest
 import torch
 
@@ -271,6 +270,24 @@ def test_product_python_wiring_on_the_fake_device(host, monkeypatch, case, into_
                  'gcbf_macbf_loss_partials', 'gcbf_macbf_loss_grads', 'gcbf_mlp_forward', 'gcbf_mlp_backward', 'gcbf_clip_adam', 'gcbf_step_bwd',
                  'gcbf_edge_attr_bwd'):
         assert name in fd.calls, name
+
+
+def test_product_train_step_on_a_batch_without_edges(host, monkeypatch):
+    """Agents out of each other's range: no edges, so no per-edge CBF values; the step must still run (action loss only; the
+    reference would produce NaN from the mean over an empty h_dot)."""
+    from gcbf_b200 import synth
+    fix = load_golden('macbf_simplecar_n20_b3')
+    sb = synth.make_states('SimpleCar', 20, 0, 2, 500.0, 3)
+    fd, env, algo = _product_algo(fix, sb, monkeypatch, host)
+    data = synth.product_batch(env, sb, torch.device('cpu'))
+    assert data.edge_index.shape[1] == 0
+    before = {k: v.clone() for k, v in algo.cbf.state_dict().items()}
+    res = algo.train_step(data)
+    s = res['scalars'].tolist()
+    want_la = float(torch.square(res['actions']).sum(dim=1).mean())
+    assert s[0] == 0.0 and s[1] == 0.0 and s[2] == 0.0 and abs(s[3] - want_la) <= 1e-7 and s[4] == 1.0 and s[5] == 1.0 and s[7] == 1.0
+    assert res['h'].shape == (0, 1) and all(torch.equal(v, before[k]) for k, v in algo.cbf.state_dict().items())      # zero CBF gradient
+    assert 'gcbf_mlp_backward' in fd.calls and 'gcbf_clip_adam' in fd.calls
 
 
 def test_factories_and_state_dict_contract():
