@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/gcbf_b200.h but not exported'
     assert sorted(_C.EXPORTED_SYMBOLS) == declared, set(_C.EXPORTED_SYMBOLS) ^ set(declared)
-    assert _C.lib().gcbf_abi_version() == 3
+    assert _C.lib().gcbf_abi_version() == 4
 
 
 def test_env_cfg_struct_layout():
