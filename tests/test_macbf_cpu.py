@@ -443,3 +443,33 @@ def test_two_gloo_ranks_equal_one_process(host, tmp_path):
         assert torch.equal(r0['cbf'][k], r1['cbf'][k]), k               # replicas stay bit-identical
     for k in r0['actor']:
         assert torch.equal(r0['actor'][k], r1['actor'][k]), k
+
+
+@pytest.mark.parametrize('env,seed', [(e, s) for e in ('SimpleCar', 'DubinsCar', 'SimpleDrone') for s in range(4)])
+def test_kernel_arithmetic_topk_properties(host, env, seed):
+    """Size-independent properties of the filtered graph: a subset of the unfiltered radius graph, sorted (target, source), in-degree
+    capped at k (k + 1 for torch_cluster's rule when the target itself is not among the first hits), identical to the unfiltered
+    graph once k covers every node, and monotone in k."""
+    from gcbf_b200 import synth
+    g = torch.Generator().manual_seed(100 + seed)
+    n = int(torch.randint(5, 40, (1,), generator=g))
+    o = 0 if env == 'SimpleCar' else (n if env == 'SimpleDrone' else int(torch.randint(0, 9, (1,), generator=g)))
+    B = int(torch.randint(1, 4, (1,), generator=g))
+    area = float(torch.rand(1, generator=g)) * 2.5 + 0.4
+    sb = synth.make_states(env, n, o, B, area, 500 + seed)
+    N = sb.nodes_per_graph
+    full = O.batch_radius_graph(env, sb.states, B, N, n)
+    full_set = set(map(tuple, full.t().tolist()))
+    prev = None
+    for k in (1, 2, 5, 12, N + 1):
+        ei, rowptr = host_topk(host, env, sb.states, B, N, n, k)
+        pairs = list(map(tuple, ei.t().tolist()))
+        assert set(pairs) <= full_set
+        assert pairs == sorted(pairs, key=lambda p: (p[1], p[0]))
+        deg = torch.bincount(ei[1], minlength=B * N) if ei.numel() else torch.zeros(1, dtype=torch.long)
+        assert int(deg.max()) <= (k + 1 if env == 'SimpleCar' else k)
+        assert torch.equal(torch.diff(rowptr.long()), deg[torch.arange(B * N).reshape(B, N)[:, :n].reshape(-1)]) if ei.numel() else True
+        if prev is not None:
+            assert prev <= set(pairs)                       # a larger k never drops an edge
+        prev = set(pairs)
+    assert prev == full_set
