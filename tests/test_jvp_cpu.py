@@ -166,3 +166,69 @@ def test_product_tangent_pass_on_a_graph_without_edges(mhost, jhost, monkeypatch
     assert ob['edge_index'].shape[1] == 0
     h, h_dot = algo.h_dot_analytic(data, torch.zeros(8, 2))
     assert h.shape == (8, 1) and float(h_dot.abs().max()) == 0.0      # h depends on the states only through the edge features
+
+
+# ---- the kernel bodies themselves on an emulated grid (tests/host_driver/cuda_emu.h) ---------------------------------------------
+@pytest.fixture(scope='module')
+def jgrid():
+    out = os.path.join(ROOT, 'tests', 'host_driver', '_build')
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, 'jvp_grid.so')
+    subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-I', os.path.join(ROOT, 'gcbf-pytorch_b200', 'csrc'),
+                           '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(ROOT, 'tests', 'host_driver'), '-o', so,
+                           os.path.join(ROOT, 'tests', 'host_driver', 'jvp_grid.cpp')])
+    return ctypes.CDLL(so)
+
+
+GEOMETRIES = [(1, 1), (3, 7), (2, 256), (1184, 256)]       # one thread striding over everything ... more threads than work
+
+
+@pytest.mark.parametrize('env_name,n,obs,B,area,seed,on_goal', CASES)
+def test_kernel_bodies_on_an_emulated_grid(jhost, jgrid, env_name, n, obs, B, area, seed, on_goal):
+    """csrc/jvp_kernels.cuh compiled as C++ and run thread by thread: every launch geometry must reproduce the serial per-element
+    driver bit for bit (indexing, pitches, grid-stride loops, untouched padding)."""
+    sb = _case(env_name, n, obs, B, area, seed, on_goal)
+    p = O.ENV_PARAMS[env_name]
+    ob = oracle_batch(sb)
+    N, sd, ed = sb.nodes_per_graph, p['state_dim'], p['edge_dim']
+    g = torch.Generator().manual_seed(seed)
+    action = (torch.randn(B * n, p['action_dim'], generator=g) * 3.0).contiguous()
+    st = torch.cat([sb.states, torch.full((B * N, 2), 9.0)], dim=1).contiguous()          # states with a pitch larger than state_dim
+    goal, uref, f = sb.goals.contiguous(), ob['u_ref'].contiguous(), ctypes.c_float
+    freeze = 1 if B == 1 else 0
+    ref = torch.full((B * N, sd + 1), 7.0)
+    jhost.host_state_dot(ENV_ID[env_name], B, N, n, _p(st), st.shape[1], _p(action), _p(uref), _p(goal), goal.shape[1], 0, f(p['action_lim']),
+                         f(p['speed_limit']), f(p['dist2goal']), freeze, _p(ref), sd + 1)
+    ei = ob['edge_index'].contiguous()
+    E = ei.shape[1]
+    t_ref = torch.full((E, ed), 7.0)
+    jhost.host_edge_attr_tangent(ENV_ID[env_name], _p(st), st.shape[1], _p(ref), sd + 1, _p(ei), ctypes.c_int64(E), _p(t_ref))
+    for grid, block in GEOMETRIES:
+        got = torch.full((B * N, sd + 1), 7.0)
+        jgrid.grid_state_dot(grid, block, ENV_ID[env_name], B, N, n, _p(st), st.shape[1], _p(action), _p(uref), _p(goal), goal.shape[1], 0,
+                             f(p['action_lim']), f(p['speed_limit']), f(p['dist2goal']), freeze, _p(got), sd + 1)
+        assert torch.equal(got, ref), (grid, block)
+        assert float(got[:, sd].min()) == 7.0                                         # the pitch padding is never written
+        if E:
+            t_got = torch.full((E, ed), 7.0)
+            jgrid.grid_edge_attr_tangent(grid, block, ENV_ID[env_name], _p(st), st.shape[1], _p(got), sd + 1, _p(ei), ctypes.c_int64(E), _p(t_got))
+            assert torch.equal(t_got, t_ref), (grid, block)
+
+
+@pytest.mark.parametrize('C,deg_hi', [(256, 9), (7, 30)])
+def test_attention_tangent_kernel_on_an_emulated_grid(jhost, jgrid, C, deg_hi):
+    g = torch.Generator().manual_seed(C + 1)
+    Nn = 29
+    deg = torch.randint(0, deg_hi + 1, (Nn,), generator=g)
+    deg[0] = 0
+    E = int(deg.sum())
+    rowptr = torch.zeros(Nn + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(deg, 0).int()
+    msg, t_msg = torch.randn(E, C + 4, generator=g), torch.randn(E, C, generator=g)        # msg with a padded pitch
+    att, t_gate = torch.rand(E, generator=g), torch.randn(E, generator=g)
+    ref = torch.full((Nn, C + 4), 7.0)
+    jhost.host_attn_aggr_tangent(_p(msg), C + 4, _p(t_msg), C, _p(att), _p(t_gate), _p(rowptr), Nn, C, _p(ref), C + 4)
+    for grid, block in GEOMETRIES:
+        got = torch.full((Nn, C + 4), 7.0)
+        jgrid.grid_attn_tangent(grid, block, _p(msg), C + 4, _p(t_msg), C, _p(att), _p(t_gate), _p(rowptr), Nn, C, _p(got), C + 4)
+        assert torch.equal(got, ref), (grid, block)
