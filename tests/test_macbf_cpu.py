@@ -473,3 +473,83 @@ def test_kernel_arithmetic_topk_properties(host, env, seed):
             assert prev <= set(pairs)                       # a larger k never drops an edge
         prev = set(pairs)
     assert prev == full_set
+
+
+# ---- the kernel bodies themselves on an emulated grid (tests/host_driver/cuda_emu.h) ---------------------------------------------
+@pytest.fixture(scope='module')
+def grid():
+    out = os.path.join(ROOT, 'tests', 'host_driver', '_build')
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, 'macbf_grid.so')
+    subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-I', os.path.join(ROOT, 'gcbf-pytorch_b200', 'csrc'),
+                           '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(ROOT, 'tests', 'host_driver'), '-o', so,
+                           os.path.join(ROOT, 'tests', 'host_driver', 'macbf_grid.cpp')])
+    return ctypes.CDLL(so)
+
+
+STRIDE_GEOMETRIES = [(1, 1), (3, 7), (2, 256), (1184, 256)]      # one thread striding over everything ... more threads than work
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_kernel_bodies_on_an_emulated_grid(host, grid, case):
+    """csrc/macbf_kernels.cuh compiled as C++ and run thread by thread: bit-equal to the per-element driver / the fixture in every launch
+    geometry (indexing, pitches, grid-stride loops, untouched padding).  The library launches the top-k kernel with 128-thread blocks,
+    one thread per target; the others as grid-stride loops over at most 8 x 148 blocks of 256."""
+    fix = load_golden(case)
+    meta, sb = _inputs(fix)
+    env, n, o, B = sb.env, sb.num_agents, sb.num_obs, sb.num_graphs
+    N, p = n + o, O.ENV_PARAMS[env]
+    f, i64 = ctypes.c_float, ctypes.c_int64
+    metric = 0 if env == 'SimpleCar' else 1
+    st = torch.cat([sb.states, torch.full((B * N, 3), 9.0)], dim=1).contiguous()           # a pitch larger than the state width
+    want_ei = fix['edge_index']
+    E = want_ei.shape[1]
+    for blocks, threads in ((-(-B * n // 128), 128), (B * n, 1), (1, 1024)):
+        if blocks * threads < B * n:
+            continue
+        rowptr = torch.zeros(B * n + 1, dtype=torch.int32)
+        grid.grid_radius_topk_count(blocks, threads, _p(st), st.shape[1], p['pos_dim'], B, N, n, f(p['comm_radius']), metric, 12, _p(rowptr))
+        rowptr[1:] = torch.cumsum(rowptr[:-1].clone(), 0).int()
+        rowptr[0] = 0
+        assert int(rowptr[-1]) == E
+        ei = torch.full((2, E), -1, dtype=torch.int64)
+        grid.grid_radius_topk_fill(blocks, threads, _p(st), st.shape[1], p['pos_dim'], B, N, n, f(p['comm_radius']), metric, 12, _p(rowptr), _p(ei), i64(E))
+        assert torch.equal(ei, want_ei), (blocks, threads)
+    ea = torch.cat([fix['edge_attr'], torch.full((E, 2), 9.0)], dim=1).contiguous()
+    R = p['radius']
+    for g_, b_ in STRIDE_GEOMETRIES:
+        safe, unsafe = torch.full((E,), 7, dtype=torch.uint8), torch.full((E,), 7, dtype=torch.uint8)
+        grid.grid_edge_masks(g_, b_, _p(ea), ea.shape[1], p['pos_dim'], i64(E), f(4 * R), f(2 * R), _p(safe), _p(unsafe))
+        assert torch.equal(safe.bool(), fix['safe_mask']) and torch.equal(unsafe.bool(), fix['unsafe_mask']) and int(safe.max()) <= 1, (g_, b_)
+    # max aggregation on this graph's CSR with random messages (padded pitches), against the per-element driver
+    gen = torch.Generator().manual_seed(1)
+    C, Nn = 37, B * N
+    rp = torch.searchsorted(want_ei[1].contiguous(), torch.arange(Nn + 1)).int()
+    msg = torch.randn(E, C + 3, generator=gen)
+    ref_out, ref_arg = torch.full((Nn, C + 1), 7.0), torch.zeros(Nn, C, dtype=torch.int32)
+    host.host_seg_max_fwd(_p(msg), C + 3, _p(rp), Nn, C, _p(ref_out), C + 1, _p(ref_arg))
+    d_out = torch.randn(Nn, C + 1, generator=gen)
+    ref_dmsg = torch.full((E, C + 2), 3.0)
+    host.host_seg_max_bwd(_p(d_out), C + 1, _p(ref_arg), Nn, C, _p(ref_dmsg), C + 2, i64(E))
+    for g_, b_ in STRIDE_GEOMETRIES:
+        out, arg = torch.full((Nn, C + 1), 7.0), torch.zeros(Nn, C, dtype=torch.int32)
+        grid.grid_seg_max_fwd(g_, b_, _p(msg), C + 3, _p(rp), Nn, C, _p(out), C + 1, _p(arg))
+        assert torch.equal(out, ref_out) and torch.equal(arg, ref_arg), (g_, b_)
+        d_msg = torch.zeros(E, C + 2)                                   # (the entry point zero-fills before the launch)
+        grid.grid_seg_max_bwd(g_, b_, _p(d_out), C + 1, _p(arg), Nn, C, _p(d_msg), C + 2)
+        assert torch.equal(d_msg, ref_dmsg), (g_, b_)
+    # loss gradients + scalars from given partial sums
+    M, ad = B * n, p['action_dim']
+    h, hn = (torch.randn(E, generator=gen) * 0.05).contiguous(), (torch.randn(E, generator=gen) * 0.05).contiguous()
+    act = torch.randn(M, ad, generator=gen).contiguous()
+    s8, u8 = fix['safe_mask'].to(torch.uint8).contiguous(), fix['unsafe_mask'].to(torch.uint8).contiguous()
+    partial = torch.zeros(16, dtype=torch.float64)
+    host.host_macbf_loss_partials(_p(h), _p(hn), _p(s8), _p(u8), i64(E), _p(act), ad, i64(M), f(1.0), f(0.02), f(0.03), _p(partial))
+    ref = [torch.zeros(E), torch.zeros(E), torch.zeros(M, ad), torch.zeros(8)]
+    host.host_macbf_loss_grads(_p(h), _p(hn), _p(s8), _p(u8), i64(E), _p(act), ad, i64(M), f(1.0), f(0.02), f(0.03), f(1.0), f(0.7), f(0.4), f(0.05),
+                               _p(partial), *[_p(t) for t in ref])
+    for g_, b_ in STRIDE_GEOMETRIES:
+        got = [torch.full((E,), 7.0), torch.full((E,), 7.0), torch.full((M, ad), 7.0), torch.full((8,), 7.0)]
+        grid.grid_macbf_loss_grads(g_, b_, _p(h), _p(hn), _p(s8), _p(u8), i64(E), _p(act), ad, i64(M), f(1.0), f(0.02), f(0.03), f(1.0), f(0.7), f(0.4),
+                                   f(0.05), _p(partial), *[_p(t) for t in got])
+        assert all(torch.equal(a, b) for a, b in zip(got, ref)), (g_, b_)
